@@ -1,0 +1,55 @@
+"""ctypes loader for lib/libhipad_dfa.so (the C ABI declared in include/hipad_dfa.h).
+
+There is no fallback of any kind: if the library is missing or a call fails, we raise.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libhipad_dfa.so")
+_lib = None
+
+_p = ctypes.c_void_p
+_i = ctypes.c_int
+_DIMS8 = [_i] * 8
+
+_SIGNATURES = {
+    "hipad_dfa_version": ([], _i),
+    "hipad_dfa_error_string": ([_i], ctypes.c_char_p),
+    "hipad_dfa_forward_f32": ([_p] * 6 + _DIMS8 + [_p], _i),
+    "hipad_dfa_forward_bf16": ([_p] * 6 + _DIMS8 + [_p], _i),
+    "hipad_dfa_backward_workspace_bytes": (_DIMS8, ctypes.c_size_t),
+    "hipad_dfa_backward_f32": ([_p] * 9 + _DIMS8 + [_p, ctypes.c_size_t, _p], _i),
+    "hipad_dfa_backward_bf16": ([_p] * 9 + _DIMS8 + [_p, ctypes.c_size_t, _p], _i),
+    "hipad_dfa_sample_indices": ([_p] * 4 + [_i] * 5 + [_p], _i),
+    "hipad_dfa_fused_forward_f32": ([_p] * 9 + _DIMS8 + [_p], _i),
+    "hipad_dfa_fused_forward_bf16": ([_p] * 9 + _DIMS8 + [_p], _i),
+}
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+
+class HipadDfaError(RuntimeError):
+    pass
+
+
+def get():
+    """Load (once) and return the ctypes handle.  Raises if the CUDA library is absent."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise HipadDfaError(
+                "hipad_dfa: %s not found. Build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(or `python hip-ad_b200/build.py`). There is no CPU or PyTorch fallback." % LIB_PATH)
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (argtypes, restype) in _SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.argtypes = argtypes
+            fn.restype = restype
+        _lib = lib
+    return _lib
+
+
+def check(status, what):
+    if status != 0:
+        msg = get().hipad_dfa_error_string(status)
+        raise HipadDfaError("%s failed with status %d: %s" % (what, status, msg.decode() if msg else "?"))

@@ -1,0 +1,375 @@
+"""Host-side mirror of the reference's deformable-aggregation MODULE interface.
+
+``DeformableFeatureAggregation`` keeps the constructor keywords, ``forward`` signature and
+state-dict keys of ``projects/mmdet3d_plugin/models/blocks.py:45-264`` so that HiP-AD configs and
+checkpoints load unchanged; the two key-point generators it is configured with
+(``models/det/blocks.py:160-248``, ``models/map/blocks.py:139-243``) are mirrored as well so the
+module is usable without mmcv.  When mmcv *is* importable the classes are also registered in its
+``ATTENTION`` / ``PLUGIN_LAYERS`` registries under the reference's names.
+
+Compute paths of ``forward`` (selected by the same ``use_deformable_func`` flag as the reference):
+  use_deformable_func=True, inference (no grad)  -> ONE fused CUDA launch: projection + group
+        softmax + aggregation (``ops.fused_deformable_aggregation``)
+  use_deformable_func=True, training             -> reference op chain with our CUDA op
+        (``ops.deformable_aggregation_function``), gradients from the deterministic backward
+  use_deformable_func=False                      -> the reference's own pure-torch grid_sample
+        branch, kept because it is part of the module's documented interface.  It is an explicit
+        opt-in, never selected automatically, and is NOT a fallback for a missing CUDA library.
+"""
+from typing import List, Optional
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ops as _ops
+
+# indices into an (undecoded) box anchor, projects/mmdet3d_plugin/core/box3d.py:1
+X, Y, Z, W, L, H, SIN_YAW, COS_YAW, VX, VY, VZ = range(11)
+
+_LOCAL_PLUGINS = {}
+
+
+def _register(cls):
+    _LOCAL_PLUGINS[cls.__name__] = cls
+    return cls
+
+
+def _build_plugin(cfg):
+    if isinstance(cfg, nn.Module):
+        return cfg
+    cfg = dict(cfg)
+    kind = cfg.pop("type")
+    if isinstance(kind, str):
+        if kind not in _LOCAL_PLUGINS:
+            try:  # anything else the user registered with mmcv
+                from mmcv.cnn.bricks.registry import PLUGIN_LAYERS
+                from mmcv.utils import build_from_cfg
+                return build_from_cfg(dict(cfg, type=kind), PLUGIN_LAYERS)
+            except ImportError as e:
+                raise KeyError("unknown plugin layer %r" % kind) from e
+        kind = _LOCAL_PLUGINS[kind]
+    return kind(**cfg)
+
+
+def linear_relu_ln(embed_dims, in_loops, out_loops, input_dims=None):
+    """blocks.py:32-42: out_loops x (in_loops x (Linear, ReLU), LayerNorm)."""
+    dims_in = embed_dims if input_dims is None else input_dims
+    layers = []
+    for _ in range(out_loops):
+        for _ in range(in_loops):
+            layers += [nn.Linear(dims_in, embed_dims), nn.ReLU(inplace=True)]
+            dims_in = embed_dims
+        layers.append(nn.LayerNorm(embed_dims))
+    return layers
+
+
+def _homogeneous_transform(points, T):
+    """points [bs,A,P,3], T [bs,4,4] -> [bs,A,P,3] (rows 0..2 of T applied to [x,y,z,1])."""
+    T = T.to(dtype=points.dtype)
+    return torch.einsum("bij,bapj->bapi", T[:, :3, :3], points) + T[:, None, None, :3, 3]
+
+
+@_register
+class SparseBox3DKeyPointsGenerator(nn.Module):
+    """Key points of a box anchor: fixed offsets scaled by exp(w,l,h) plus learnable ones,
+    rotated by yaw and translated to the box centre (det/blocks.py:160-248)."""
+
+    def __init__(self, embed_dims=256, num_learnable_pts=0, fix_scale=None):
+        super().__init__()
+        self.embed_dims = embed_dims
+        self.num_learnable_pts = num_learnable_pts
+        if fix_scale is None:
+            fix_scale = ((0.0, 0.0, 0.0),)
+        self.fix_scale = nn.Parameter(torch.tensor(fix_scale, dtype=torch.float32), requires_grad=False)
+        self.num_pts = len(self.fix_scale) + num_learnable_pts
+        if num_learnable_pts > 0:
+            self.learnable_fc = nn.Linear(embed_dims, num_learnable_pts * 3)
+
+    def init_weight(self):
+        if self.num_learnable_pts > 0:
+            nn.init.xavier_uniform_(self.learnable_fc.weight)
+            nn.init.constant_(self.learnable_fc.bias, 0.0)
+
+    def forward(self, anchor, instance_feature=None, T_cur2temp_list=None,
+                cur_timestamp=None, temp_timestamps=None):
+        # NB: DeformableFeatureAggregation calls this as (anchor, anchor_embed, instance_feature):
+        # the learnable offsets are driven by the anchor embedding.
+        bs, num_anchor = anchor.shape[:2]
+        size = anchor[..., None, [W, L, H]].exp()
+        key_points = self.fix_scale * size
+        if self.num_learnable_pts > 0 and instance_feature is not None:
+            scale = self.learnable_fc(instance_feature).reshape(bs, num_anchor, self.num_learnable_pts, 3)
+            key_points = torch.cat([key_points, (scale.sigmoid() - 0.5) * size], dim=-2)
+        cos, sin = anchor[..., None, COS_YAW], anchor[..., None, SIN_YAW]
+        kx, ky, kz = key_points.unbind(-1)
+        key_points = torch.stack([cos * kx - sin * ky, sin * kx + cos * ky, kz], dim=-1)
+        key_points = key_points + anchor[..., None, [X, Y, Z]]
+
+        if (cur_timestamp is None or temp_timestamps is None or T_cur2temp_list is None
+                or len(temp_timestamps) == 0):
+            return key_points
+        velocity = anchor[..., VX:]
+        temp_list = []
+        for T, t_time in zip(T_cur2temp_list, temp_timestamps):
+            dt = (cur_timestamp - t_time).to(dtype=velocity.dtype)
+            moved = key_points - (velocity * dt[:, None, None])[:, :, None]
+            temp_list.append(_homogeneous_transform(moved, T))
+        return key_points, temp_list
+
+
+@_register
+class SparsePoint3DKeyPointsGenerator(nn.Module):
+    """Key points of a poly-line / waypoint anchor: every 2-D sample point gets
+    len(fix_height) x num_learnable_pts learned planar offsets at fixed heights above
+    ``ground_height`` (map/blocks.py:139-243).  Used by the map queries and by the
+    planning deformable attention."""
+
+    def __init__(self, embed_dims: int = 256, num_sample: int = 20, num_learnable_pts: int = 0,
+                 fix_height=(0,), ground_height=0, with_points_embed: bool = False,
+                 with_anchor_embed: bool = False):
+        super().__init__()
+        self.embed_dims = embed_dims
+        self.num_sample = num_sample
+        self.num_learnable_pts = num_learnable_pts
+        self.with_points_embed = with_points_embed
+        self.with_anchor_embed = with_anchor_embed
+        n_h = len(fix_height)
+        self.num_pts = n_h * num_learnable_pts * (1 if with_points_embed else num_sample)
+        if num_learnable_pts > 0:
+            self.learnable_fc = nn.Linear(embed_dims, self.num_pts * 2)
+        self.fix_height = tuple(float(h) for h in fix_height)
+        self.ground_height = ground_height
+
+    def init_weight(self):
+        if self.num_learnable_pts > 0:
+            nn.init.xavier_uniform_(self.learnable_fc.weight)
+            nn.init.constant_(self.learnable_fc.bias, 0.0)
+
+    def forward(self, anchor, anchor_embed=None, instance_feature=None, T_cur2temp_list=None,
+                cur_timestamp=None, temp_timestamps=None):
+        assert self.num_learnable_pts > 0, "No learnable pts"
+        bs, num_anchor, _ = anchor.shape
+        n_h = len(self.fix_height)
+        if self.with_anchor_embed:
+            if self.with_points_embed:
+                src = instance_feature.repeat(1, self.num_sample, 1) + anchor_embed
+            else:
+                src = instance_feature + anchor_embed
+        else:
+            src = instance_feature
+        offset = self.learnable_fc(src).reshape(bs, num_anchor, self.num_sample, n_h, self.num_learnable_pts, 2)
+        xy = offset + anchor.view(bs, num_anchor, self.num_sample, 1, 1, 2)
+        heights = xy.new_tensor(self.fix_height).view(1, 1, 1, n_h, 1, 1)
+        z = (xy.new_full(xy.shape[:-1] + (1,), float(self.ground_height)) + heights)
+        key_points = torch.cat([xy, z], dim=-1).flatten(2, 4)
+
+        if (cur_timestamp is None or temp_timestamps is None or T_cur2temp_list is None
+                or len(temp_timestamps) == 0):
+            return key_points
+        return key_points, [_homogeneous_transform(key_points, T) for T in T_cur2temp_list]
+
+
+class DeformableFeatureAggregation(nn.Module):
+    def __init__(
+        self,
+        embed_dims: int = 256,
+        num_groups: int = 8,
+        num_levels: int = 4,
+        num_sample: int = 20,
+        num_cams: int = 6,
+        proj_drop: float = 0.0,
+        attn_drop: float = 0.0,
+        kps_generator: dict = None,
+        temporal_fusion_module=None,
+        use_temporal_anchor_embed=True,
+        use_deformable_func=False,
+        use_camera_embed=False,
+        use_points_embed=False,
+        use_anchor_embed=False,
+        residual_mode="add",
+        fused_inference=True,
+    ):
+        super().__init__()
+        if embed_dims % num_groups != 0:
+            raise ValueError(
+                f"embed_dims must be divisible by num_groups, but got {embed_dims} and {num_groups}")
+        self.group_dims = embed_dims // num_groups
+        self.num_cams = num_cams
+        self.num_levels = num_levels
+        self.num_groups = num_groups
+        self.num_sample = num_sample
+        self.embed_dims = embed_dims
+        self.use_points_embed = use_points_embed
+        self.use_camera_embed = use_camera_embed
+        self.use_deformable_func = use_deformable_func
+        self.use_temporal_anchor_embed = use_temporal_anchor_embed
+        self.fused_inference = fused_inference
+        self.attn_drop = attn_drop
+        self.residual_mode = residual_mode
+        self.proj_drop = nn.Dropout(proj_drop)
+
+        if not isinstance(kps_generator, nn.Module):
+            kps_generator = dict(kps_generator)
+            kps_generator["embed_dims"] = embed_dims
+            if use_points_embed:
+                kps_generator["with_points_embed"] = use_points_embed
+            if use_anchor_embed:
+                kps_generator["with_anchor_embed"] = use_anchor_embed
+        self.kps_generator = _build_plugin(kps_generator)
+        self.kps_pts = self.kps_generator.num_pts
+        self.num_pts = self.kps_pts * num_sample if use_points_embed else self.kps_pts
+
+        if temporal_fusion_module is not None:
+            if not isinstance(temporal_fusion_module, nn.Module):
+                temporal_fusion_module = dict(temporal_fusion_module)
+                temporal_fusion_module.setdefault("embed_dims", embed_dims)
+            self.temp_module = _build_plugin(temporal_fusion_module)
+        else:
+            self.temp_module = None
+        self.output_proj = nn.Linear(embed_dims, embed_dims)
+
+        input_dims = embed_dims * num_sample if use_points_embed else embed_dims
+        n_w = num_groups * num_levels * self.num_pts
+        if use_camera_embed:
+            self.camera_encoder = nn.Sequential(*linear_relu_ln(embed_dims, 1, 2, 12))
+            if use_points_embed:
+                self.weights_fc = nn.Sequential(
+                    nn.Linear(input_dims, input_dims // 2), nn.ReLU(),
+                    nn.Linear(input_dims // 2, n_w), nn.ReLU(),
+                    nn.Linear(n_w, n_w))
+            else:
+                self.weights_fc = nn.Linear(input_dims, n_w)
+        else:
+            self.camera_encoder = None
+            self.weights_fc = nn.Linear(input_dims, n_w * num_cams)
+
+    def init_weight(self):
+        if isinstance(self.weights_fc, nn.Linear):
+            nn.init.constant_(self.weights_fc.weight, 0.0)
+            nn.init.constant_(self.weights_fc.bias, 0.0)
+        nn.init.xavier_uniform_(self.output_proj.weight)
+        nn.init.constant_(self.output_proj.bias, 0.0)
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, instance_feature: torch.Tensor, anchor: torch.Tensor, anchor_embed: torch.Tensor,
+                feature_maps: List[torch.Tensor], metas: dict, **kwargs):
+        bs, num_anchor = instance_feature.shape[:2]
+        key_points = self.kps_generator(anchor, anchor_embed, instance_feature)
+
+        if self.use_deformable_func:
+            dropping = self.training and self.attn_drop > 0
+            fusable = (self.fused_inference and not dropping and not torch.is_grad_enabled()
+                       and 128 % self.num_groups == 0)
+            if fusable:
+                logits = self._get_logits(instance_feature, anchor_embed, metas)
+                features = _ops.fused_deformable_aggregation(
+                    feature_maps, key_points, metas["projection_mat"], metas.get("image_wh"), logits)
+            else:
+                weights = self._get_weights(instance_feature, anchor_embed, metas)
+                points_2d = (
+                    self.project_points(key_points, metas["projection_mat"], metas.get("image_wh"))
+                    .permute(0, 2, 3, 1, 4)
+                    .reshape(bs, num_anchor, self.num_pts, self.num_cams, 2)
+                )
+                weights = weights.permute(0, 1, 4, 2, 3, 5).contiguous().reshape(
+                    bs, num_anchor, self.num_pts, self.num_cams, self.num_levels, self.num_groups)
+                features = _ops.deformable_aggregation_function(*feature_maps, points_2d, weights)
+            features = features.reshape(bs, num_anchor, self.embed_dims)
+        else:
+            weights = self._get_weights(instance_feature, anchor_embed, metas)
+            features = self.feature_sampling(
+                feature_maps, key_points, metas["projection_mat"], metas.get("image_wh"))
+            features = self.multi_view_level_fusion(features, weights)
+            features = features.sum(dim=2)
+        output = self.proj_drop(self.output_proj(features))
+        if self.residual_mode == "add":
+            output = output + instance_feature
+        elif self.residual_mode == "cat":
+            output = torch.cat([output, instance_feature], dim=-1)
+        return output
+
+    def _get_logits(self, instance_feature, anchor_embed, metas=None):
+        """Raw ``weights_fc`` output [bs, A, cams, G*L*P] (blocks.py:178-199, before the softmax)."""
+        bs, num_anchor = instance_feature.shape[:2]
+        if self.use_points_embed:
+            feature = instance_feature.repeat(1, self.num_sample, 1) + anchor_embed
+            if self.camera_encoder is not None:
+                cam = self.camera_encoder(metas["projection_mat"][:, :, :3].reshape(bs, self.num_cams, -1))
+                feature = feature[:, :, None] + cam[:, None]
+                feature = feature.view(bs, num_anchor, self.num_sample, self.num_cams, -1)
+                feature = feature.permute(0, 1, 3, 2, 4).reshape(bs, num_anchor, self.num_cams, -1)
+            else:
+                feature = feature.view(bs, num_anchor, self.num_sample, self.num_cams, -1)
+                feature = feature.reshape(bs, num_anchor, -1)
+        else:
+            feature = instance_feature + anchor_embed
+            if self.camera_encoder is not None:
+                cam = self.camera_encoder(metas["projection_mat"][:, :, :3].reshape(bs, self.num_cams, -1))
+                feature = feature[:, :, None] + cam[:, None]
+        return self.weights_fc(feature)
+
+    def _get_weights(self, instance_feature, anchor_embed, metas=None):
+        """Softmax over cams*levels*points per group -> [bs, A, cams, L, P, G] (blocks.py:178-214)."""
+        bs, num_anchor = instance_feature.shape[:2]
+        weights = (
+            self._get_logits(instance_feature, anchor_embed, metas)
+            .reshape(bs, num_anchor, -1, self.num_groups)
+            .softmax(dim=-2)
+            .reshape(bs, num_anchor, self.num_cams, self.num_levels, self.num_pts, self.num_groups)
+        )
+        if self.training and self.attn_drop > 0:
+            # the reference draws this mask on the CPU and copies it over every call
+            # (blocks.py:210-211); we draw it on the device: same distribution, no H2D copy.
+            mask = torch.rand(bs, num_anchor, self.num_cams, 1, self.num_pts, 1,
+                              device=weights.device, dtype=weights.dtype)
+            weights = ((mask > self.attn_drop) * weights) / (1 - self.attn_drop)
+        return weights
+
+    @staticmethod
+    def project_points(key_points, projection_mat, image_wh=None):
+        """[bs,A,P,3] -> [bs,cams,A,P,2], pixel coords / image_wh (blocks.py:217-225)."""
+        pts = torch.cat([key_points, torch.ones_like(key_points[..., :1])], dim=-1)
+        cam = torch.matmul(projection_mat[:, :, None, None], pts[:, None, ..., None]).squeeze(-1)
+        xy = cam[..., :2] / torch.clamp(cam[..., 2:3], min=1e-5)
+        if image_wh is not None:
+            xy = xy / image_wh[:, :, None, None]
+        return xy
+
+    @staticmethod
+    def feature_sampling(feature_maps: List[torch.Tensor], key_points: torch.Tensor,
+                         projection_mat: torch.Tensor, image_wh: Optional[torch.Tensor] = None):
+        """grid_sample branch (blocks.py:227-251): -> [bs, A, cams, L, P, C]."""
+        num_levels = len(feature_maps)
+        num_cams = feature_maps[0].shape[1]
+        bs, num_anchor, num_pts = key_points.shape[:3]
+        grid = DeformableFeatureAggregation.project_points(key_points, projection_mat, image_wh)
+        grid = (grid * 2 - 1).flatten(end_dim=1)
+        sampled = torch.stack(
+            [F.grid_sample(fm.flatten(end_dim=1), grid, mode="bilinear", padding_mode="zeros",
+                           align_corners=False) for fm in feature_maps], dim=1)
+        return sampled.reshape(bs, num_cams, num_levels, -1, num_anchor, num_pts).permute(0, 4, 1, 2, 5, 3)
+
+    def multi_view_level_fusion(self, features: torch.Tensor, weights: torch.Tensor):
+        bs, num_anchor = weights.shape[:2]
+        grouped = features.reshape(features.shape[:-1] + (self.num_groups, self.group_dims))
+        fused = (weights[..., None] * grouped).sum(dim=2).sum(dim=2)
+        return fused.reshape(bs, num_anchor, self.num_pts, self.embed_dims)
+
+
+def _register_with_mmcv():
+    try:
+        from mmcv.cnn.bricks.registry import ATTENTION, PLUGIN_LAYERS
+    except Exception:
+        return False
+    for reg, cls in ((ATTENTION, DeformableFeatureAggregation),
+                     (PLUGIN_LAYERS, SparseBox3DKeyPointsGenerator),
+                     (PLUGIN_LAYERS, SparsePoint3DKeyPointsGenerator)):
+        try:
+            reg.register_module(module=cls, force=True)
+        except Exception:
+            pass
+    return True
+
+
+_register_with_mmcv()

@@ -1,0 +1,64 @@
+// dfa_dispatch.cuh — host-side template dispatch for the sample-major kernel family.
+#pragma once
+#include "dfa_launch.h"
+#include "dfa_sample.cuh"
+
+namespace hipad {
+
+constexpr int kSampleWarps = 4;
+constexpr int kMaxPairsPerSlice = 8192;
+
+template <typename K>
+inline cudaError_t ensure_smem(K kern, size_t smem) {
+    if (smem <= 48 * 1024) return cudaSuccess;
+    // attribute is per device and per function; setting it is idempotent and cheap
+    return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+}
+
+template <typename T, int V, int NCH, int kL, int kMode, bool kShfl, bool kCluster>
+int launch_sample_inst(const SampleParams& p, int grid, size_t smem, cudaStream_t st) {
+    auto kern = dfa_sample_kernel<T, V, NCH, kL, kMode, kShfl, kCluster, kSampleWarps>;
+    cudaError_t e = ensure_smem(kern, smem);
+    if (e != cudaSuccess) return (int)e;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid, 1, 1);
+    cfg.blockDim = dim3(kSampleWarps * 32, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    if (kCluster) {
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = (unsigned)p.S;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+    }
+    e = cudaLaunchKernelEx(&cfg, kern, p);
+    return (int)e;
+}
+
+template <typename T, int kMode, bool kCluster>
+int dispatch_sample(const SampleParams& p, KernelShape ks, int grid, size_t smem, cudaStream_t st) {
+    constexpr int VV = 16 / (int)sizeof(T);
+    const bool l4 = (p.d.L == 4);
+#define HIPAD_CASE(V_, NCH_, KL_, SHFL_) \
+    return launch_sample_inst<T, V_, NCH_, KL_, kMode, SHFL_, kCluster>(p, grid, smem, st)
+    if (ks.vector) {
+        if (ks.nch == 1) { if (l4) HIPAD_CASE(VV, 1, 4, true); else HIPAD_CASE(VV, 1, 0, true); }
+        if (ks.nch == 2) { if (l4) HIPAD_CASE(VV, 2, 4, true); else HIPAD_CASE(VV, 2, 0, true); }
+        if (ks.nch == 4) { if (l4) HIPAD_CASE(VV, 4, 4, true); else HIPAD_CASE(VV, 4, 0, true); }
+    } else {
+        if (ks.nch == 2) HIPAD_CASE(1, 2, 0, false);
+        if (ks.nch == 8) HIPAD_CASE(1, 8, 0, false);
+    }
+#undef HIPAD_CASE
+    return -2;
+}
+
+inline size_t sample_smem_for(int mode, const Dims& d, KernelShape ks, ElemType t, int ps) {
+    const int V = ks.vector ? (t == kF32 ? 4 : 8) : 1;
+    return sample_smem_bytes<kSampleWarps>(mode, d.cams * d.L, ks.nch * 32 * V, ps, d.G, d.cams);
+}
+
+}  // namespace hipad

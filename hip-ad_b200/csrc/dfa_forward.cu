@@ -1,0 +1,103 @@
+// dfa_forward.cu — forward launchers (plain 5-argument contract and fused projection+softmax).
+#include "dfa_dispatch.cuh"
+
+namespace hipad {
+
+KernelShape pick_shape(ElemType t, int C, int G, bool aligned16) {
+    KernelShape ks{false, 0, false};
+    const int V = (t == kF32) ? 4 : 8;
+    const int gd = C / G;
+    const bool pow2_lanes = (gd % V == 0) && (((gd / V) & ((gd / V) - 1)) == 0) && (gd / V) <= 32;
+    if (aligned16 && C % V == 0 && pow2_lanes && C <= 4 * 32 * V) {
+        ks.vector = true;
+        const int chunks = (C + 32 * V - 1) / (32 * V);
+        ks.nch = chunks <= 1 ? 1 : (chunks <= 2 ? 2 : 4);
+        ks.ok = true;
+        return ks;
+    }
+    if (C <= 256) {
+        ks.vector = false;
+        ks.nch = (C <= 64) ? 2 : 8;
+        ks.ok = true;
+    }
+    return ks;
+}
+
+int choose_slices(long long rows, int pairs, int target_ctas) {
+    int S = 1;
+    while (S < 8 && rows * S < target_ctas && pairs / (S * 2) >= 64) S *= 2;
+    while (S < 8 && (pairs + S - 1) / S > kMaxPairsPerSlice) S *= 2;
+    return S;
+}
+
+int launch_forward(const FwdArgs& a) {
+    const Dims& d = a.d;
+    const bool al = (reinterpret_cast<uintptr_t>(a.feat) % 16 == 0) &&
+                    (reinterpret_cast<uintptr_t>(a.out) % 16 == 0);
+    const KernelShape ks = pick_shape(a.type, d.C, d.G, al);
+    if (!ks.ok || d.cams * d.L > kMaxCamLevels) return -2;
+    const int mode = a.fused ? kFused : kFwd;
+    if (a.fused && ((kSampleWarps * 32) % d.G != 0)) return -2;
+
+    SampleParams p = {};
+    p.feat = a.feat; p.shapes = a.shapes; p.starts = a.starts;
+    p.loc = a.loc; p.weights = a.weights; p.out = a.out;
+    p.key_points = a.key_points; p.proj = a.proj; p.image_wh = a.image_wh; p.loc_out = a.loc_out;
+    p.d = d;
+    const int NP = d.P * d.cams;
+    const long long rows = (long long)d.bs * d.A;
+    p.S = choose_slices(rows, NP, 4 * 148);
+    p.PS = (NP + p.S - 1) / p.S;
+    if (p.PS > kMaxPairsPerSlice) return -2;
+    const long long grid = rows * p.S;
+    if (grid > 0x7fffffffLL) return -2;
+    const size_t smem = sample_smem_for(mode, d, ks, a.type, p.PS);
+
+#define HIPAD_GO(T_, MODE_)                                                                  \
+    return (p.S > 1) ? dispatch_sample<T_, MODE_, true>(p, ks, (int)grid, smem, a.stream)    \
+                     : dispatch_sample<T_, MODE_, false>(p, ks, (int)grid, smem, a.stream)
+    if (a.type == kF32) {
+        if (a.fused) HIPAD_GO(float, kFused); else HIPAD_GO(float, kFwd);
+    } else {
+        if (a.fused) HIPAD_GO(__nv_bfloat16, kFused); else HIPAD_GO(__nv_bfloat16, kFwd);
+    }
+#undef HIPAD_GO
+}
+
+// ------------------------------------------------------------------ integer sampling contract
+__global__ void dfa_indices_kernel(int32_t* __restrict__ idx, const int* __restrict__ shapes,
+                                   const int* __restrict__ starts, const float* __restrict__ loc,
+                                   long long n_sample, int cams, int L) {
+    const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_sample) return;
+    const int cam = (int)(s % cams);
+    const float2 xy = __ldg(reinterpret_cast<const float2*>(loc) + s);
+    const bool vis = loc_valid(xy.x, xy.y);
+    for (int l = 0; l < L; ++l) {
+        const int cl = cam * L + l;
+        const int h = __ldg(shapes + cl * 2), w = __ldg(shapes + cl * 2 + 1), st = __ldg(starts + cl);
+        int32_t* o = idx + (s * L + l) * 6;
+        o[0] = vis ? 1 : 0;
+        o[3] = st;
+        if (vis) {
+            const Quad q = quad_setup(xy.x, xy.y, h, w);
+            o[1] = q.h_low;
+            o[2] = q.w_low;
+            o[4] = (int)q.ok1 | ((int)q.ok2 << 1) | ((int)q.ok3 << 2) | ((int)q.ok4 << 3);
+            o[5] = st + q.h_low * w + q.w_low;
+        } else {
+            o[1] = 0; o[2] = 0; o[4] = 0; o[5] = 0;
+        }
+    }
+}
+
+int launch_indices(int32_t* idx, const int* shapes, const int* starts, const float* loc, int bs, int cams, int L,
+                   int A, int P, cudaStream_t stream) {
+    const long long n = (long long)bs * A * P * cams;
+    const long long blocks = (n + 255) / 256;
+    if (blocks > 0x7fffffffLL) return -2;
+    dfa_indices_kernel<<<(unsigned)blocks, 256, 0, stream>>>(idx, shapes, starts, loc, n, cams, L);
+    return (int)cudaGetLastError();
+}
+
+}  // namespace hipad

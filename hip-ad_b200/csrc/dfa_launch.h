@@ -1,0 +1,64 @@
+// dfa_launch.h — internal launch interface between the C ABI (dfa_api.cu) and the kernel
+// translation units (dfa_forward.cu, dfa_backward.cu).  Not installed; see include/hipad_dfa.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include "dfa_common.cuh"
+
+namespace hipad {
+
+enum ElemType { kF32 = 0, kBF16 = 1 };
+
+struct KernelShape {
+    bool vector;   // 16-byte vector path (V = 4 fp32 / 8 bf16) vs scalar path (V = 1)
+    int nch;       // 32-lane channel chunks per row
+    bool ok;
+};
+
+// picks the kernel family member for (C, G, alignment); ok=false -> HIPAD_DFA_ERR_UNSUPPORTED
+KernelShape pick_shape(ElemType t, int C, int G, bool aligned16);
+int choose_slices(long long rows, int pairs, int target_ctas);
+
+struct FwdArgs {
+    ElemType type;
+    float* out;
+    const void* feat;
+    const int* shapes;
+    const int* starts;
+    const float* loc;       // unfused
+    const float* weights;   // unfused: softmaxed weights; fused: logits
+    const float* key_points;
+    const float* proj;
+    const float* image_wh;
+    float* loc_out;
+    bool fused;
+    Dims d;
+    cudaStream_t stream;
+};
+int launch_forward(const FwdArgs& a);
+
+struct BwdArgs {
+    ElemType type;
+    const void* feat;
+    const int* shapes;
+    const int* starts;
+    const float* loc;
+    const float* weights;
+    const float* grad_out;
+    void* g_feat;
+    float* g_loc;
+    float* g_w;
+    Dims d;
+    void* workspace;
+    size_t workspace_bytes;
+    cudaStream_t stream;
+};
+int launch_backward(const BwdArgs& a);
+size_t backward_workspace_bytes(const Dims& d);
+
+int launch_indices(int32_t* idx, const int* shapes, const int* starts, const float* loc, int bs, int cams, int L,
+                   int A, int P, cudaStream_t stream);
+
+}  // namespace hipad

@@ -1,0 +1,164 @@
+"""autograd boundary of the B200 deformable aggregation op.
+
+Mirrors ``projects/mmdet3d_plugin/ops/deformable_aggregation.py:7-75`` of HiP-AD: same class
+name, same ``apply(mc_ms_feat, spatial_shape, scale_start_index, sampling_location, weights)``
+signature, same 5-tuple of gradients ``(g_feat, None, None, g_loc, g_w)``.  The work is done by
+hand-written sm_100a kernels behind the C ABI of ``include/hipad_dfa.h`` (loaded with ctypes);
+there is no other implementation to fall back to.
+
+Differences from the reference, all behind the same interface:
+  * launches go to the CURRENT torch stream (the reference uses the legacy default stream), so the
+    op is correct under side streams and capturable in CUDA graphs;
+  * bf16 feature maps are consumed as stored (fp32 accumulate, fp32 output) instead of being
+    up-cast to a fp32 copy; every other float dtype is normalised to fp32 like the reference;
+  * outputs / gradients are written in full by the kernels: no zero-fill passes, no atomics,
+    bitwise reproducible run to run;
+  * ``ctx.needs_input_grad`` is honoured: the dense feature gradient is skipped when the
+    feature maps do not require grad (the reference always computes all three).
+"""
+import torch
+from torch.autograd.function import Function, once_differentiable
+
+from .. import _lib
+
+
+def _as_i32(t):
+    cached = getattr(t, "_hipad_i32", None)
+    if cached is not None and cached.device == t.device:
+        return cached
+    return t.contiguous().int()
+
+
+def _require_cuda(*tensors):
+    for t in tensors:
+        if not t.is_cuda:
+            raise _lib.HipadDfaError(
+                "hipad_dfa: all tensors must live on a CUDA device (got %s); there is no CPU path" % t.device)
+
+
+def _dims(feat, shapes, loc, weights):
+    bs, num_feat, C = feat.shape
+    cams, L = shapes.shape[:2]
+    A, P = loc.shape[1:3]
+    G = weights.shape[-1]
+    if tuple(loc.shape) != (bs, A, P, cams, 2):
+        raise ValueError("sampling_location must be [bs, anchors, pts, cams, 2], got %s" % (tuple(loc.shape),))
+    if weights.numel() != bs * A * P * cams * L * G:
+        raise ValueError("weights must be [bs, anchors, pts, cams, levels, groups], got %s" % (tuple(weights.shape),))
+    return bs, cams, num_feat, C, L, A, P, G
+
+
+def _norm_feat(feat):
+    if feat.dtype == torch.bfloat16:
+        return feat.contiguous()
+    return feat.contiguous().float()
+
+
+class DeformableAggregationFunction(Function):
+    @staticmethod
+    def forward(ctx, mc_ms_feat, spatial_shape, scale_start_index, sampling_location, weights):
+        lib = _lib.get()
+        _require_cuda(mc_ms_feat, spatial_shape, scale_start_index, sampling_location, weights)
+        feat = _norm_feat(mc_ms_feat)
+        shapes = _as_i32(spatial_shape)
+        starts = _as_i32(scale_start_index)
+        loc = sampling_location.contiguous().float()
+        w = weights.contiguous().float()
+        dims = _dims(feat, shapes, loc, w)
+        bs, _, _, C, _, A, _, _ = dims
+        with torch.cuda.device(feat.device):
+            out = torch.empty((bs, A, C), dtype=torch.float32, device=feat.device)
+            stream = torch.cuda.current_stream().cuda_stream
+            fn = lib.hipad_dfa_forward_bf16 if feat.dtype == torch.bfloat16 else lib.hipad_dfa_forward_f32
+            rc = fn(out.data_ptr(), feat.data_ptr(), shapes.data_ptr(), starts.data_ptr(),
+                    loc.data_ptr(), w.data_ptr(), *dims, stream)
+        _lib.check(rc, "hipad_dfa_forward")
+        ctx.save_for_backward(feat, shapes, starts, loc, w)
+        ctx.feat_dtype = mc_ms_feat.dtype
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_output):
+        lib = _lib.get()
+        feat, shapes, starts, loc, w = ctx.saved_tensors
+        dims = _dims(feat, shapes, loc, w)
+        need_feat = ctx.needs_input_grad[0]
+        go = grad_output.contiguous().float()
+        with torch.cuda.device(feat.device):
+            g_feat = torch.empty_like(feat) if need_feat else None
+            g_loc = torch.empty_like(loc)
+            g_w = torch.empty_like(w)
+            nbytes = lib.hipad_dfa_backward_workspace_bytes(*dims)
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=feat.device)
+            stream = torch.cuda.current_stream().cuda_stream
+            fn = lib.hipad_dfa_backward_bf16 if feat.dtype == torch.bfloat16 else lib.hipad_dfa_backward_f32
+            rc = fn(feat.data_ptr(), shapes.data_ptr(), starts.data_ptr(), loc.data_ptr(), w.data_ptr(),
+                    go.data_ptr(), g_feat.data_ptr() if need_feat else None, g_loc.data_ptr(), g_w.data_ptr(),
+                    *dims, ws.data_ptr(), nbytes, stream)
+        _lib.check(rc, "hipad_dfa_backward")
+        if need_feat and g_feat.dtype != ctx.feat_dtype:
+            g_feat = g_feat.to(ctx.feat_dtype)
+        return g_feat, None, None, g_loc, g_w
+
+
+# import-compatibility alias (ops/__init__.py:3-4 of the reference exports both names; the A800
+# twin there is the same source bound to a second build, selected by GPU name string)
+DeformableAggregationFunctionA800 = DeformableAggregationFunction
+
+
+def fused_deformable_aggregation(feature_maps, key_points, projection_mat, image_wh, logits,
+                                 return_locations=False):
+    """Inference-only fused forward: projection + group softmax + aggregation in one launch.
+
+    feature_maps : the triple from ``feature_maps_format`` ([col_feats, spatial_shape, scale_start_index])
+    key_points   : [bs, A, P, 3]          (``kps_generator`` output)
+    projection_mat [bs, cams, 4, 4], image_wh [bs, cams, 2] or None   (``metas``)
+    logits       : [bs, A, cams, L*P*G]   raw ``weights_fc`` output, BEFORE softmax (blocks.py:196-199)
+    returns      : [bs, A, C] float32  (+ sampling locations [bs, A, P, cams, 2] if requested)
+    """
+    lib = _lib.get()
+    col_feats, spatial_shape, scale_start_index = feature_maps
+    _require_cuda(col_feats, key_points, projection_mat, logits)
+    feat = _norm_feat(col_feats)
+    shapes = _as_i32(spatial_shape)
+    starts = _as_i32(scale_start_index)
+    kp = key_points.contiguous().float()
+    pm = projection_mat.contiguous().float()
+    wh = image_wh.contiguous().float() if image_wh is not None else None
+    lg = logits.contiguous().float()
+    bs, num_feat, C = feat.shape
+    cams, L = shapes.shape[:2]
+    A, P = kp.shape[1:3]
+    G = lg.numel() // (bs * A * cams * L * P)
+    if lg.numel() != bs * A * cams * L * P * G or G == 0:
+        raise ValueError("logits must hold bs*A*cams*L*P*G elements, got %s" % (tuple(lg.shape),))
+    dims = (bs, cams, num_feat, C, L, A, P, G)
+    with torch.cuda.device(feat.device):
+        out = torch.empty((bs, A, C), dtype=torch.float32, device=feat.device)
+        loc = torch.empty((bs, A, P, cams, 2), dtype=torch.float32, device=feat.device) if return_locations else None
+        stream = torch.cuda.current_stream().cuda_stream
+        fn = lib.hipad_dfa_fused_forward_bf16 if feat.dtype == torch.bfloat16 else lib.hipad_dfa_fused_forward_f32
+        rc = fn(out.data_ptr(), feat.data_ptr(), shapes.data_ptr(), starts.data_ptr(), kp.data_ptr(), pm.data_ptr(),
+                wh.data_ptr() if wh is not None else None, lg.data_ptr(),
+                loc.data_ptr() if loc is not None else None, *dims, stream)
+    _lib.check(rc, "hipad_dfa_fused_forward")
+    return (out, loc) if return_locations else out
+
+
+def sample_indices(spatial_shape, scale_start_index, sampling_location):
+    """int32 [bs, A, P, cams, L, 6] = (valid, h_low, w_low, level_offset, corner_mask, row0) exactly as
+    the kernels compute them (the bit-exact integer contract checked against the oracle)."""
+    lib = _lib.get()
+    _require_cuda(spatial_shape, scale_start_index, sampling_location)
+    shapes = _as_i32(spatial_shape)
+    starts = _as_i32(scale_start_index)
+    loc = sampling_location.contiguous().float()
+    bs, A, P, cams, _ = loc.shape
+    L = shapes.shape[1]
+    with torch.cuda.device(loc.device):
+        idx = torch.empty((bs, A, P, cams, L, 6), dtype=torch.int32, device=loc.device)
+        rc = lib.hipad_dfa_sample_indices(idx.data_ptr(), shapes.data_ptr(), starts.data_ptr(), loc.data_ptr(),
+                                          bs, cams, L, A, P, torch.cuda.current_stream().cuda_stream)
+    _lib.check(rc, "hipad_dfa_sample_indices")
+    return idx

@@ -1,0 +1,145 @@
+/*
+ * hipad_dfa.h — C ABI of the B200-native deformable feature aggregation (DFA).
+ *
+ * This is the drop-in boundary for HiP-AD's hot path.  Every entry point takes
+ * plain device pointers + sizes + a CUDA stream and returns an int status
+ * (0 = success, >0 = cudaError_t value, <0 = HIPAD_DFA_ERR_*).  No torch types,
+ * no global state, no hidden allocation: the caller owns every buffer,
+ * including the backward workspace.  All launches go to the given stream and
+ * are CUDA-graph capturable (no host synchronisation, no legacy-stream use).
+ *
+ * Reference interfaces replaced (paths relative to the HiP-AD repository):
+ *   projects/mmdet3d_plugin/ops/src/deformable_aggregation_cuda.cu:265-288
+ *       void deformable_aggregation(float* output, const float* mc_ms_feat, ...)
+ *       -> hipad_dfa_forward_f32 / _bf16
+ *   projects/mmdet3d_plugin/ops/src/deformable_aggregation_cuda.cu:291-318
+ *       void deformable_aggregation_grad(const float* mc_ms_feat, ..., float* grad_weights, ...)
+ *       -> hipad_dfa_backward_f32 / _bf16 (+ hipad_dfa_backward_workspace_bytes)
+ *   projects/mmdet3d_plugin/ops/src/deformable_aggregation.cpp:31-62, 86-124
+ *       ATen glue (shape extraction, at::zeros) -> done by the Python host
+ *       (hip-ad_b200/ops/deformable_aggregation.py) on top of this ABI.
+ *
+ * Tensor layouts (row-major, identical to the reference, deformable_aggregation.cpp:22-28):
+ *   mc_ms_feat        [bs, num_feat, num_embeds]               f32 or bf16
+ *   spatial_shape     [num_cams, num_scale, 2]  (h, w)         int32, device
+ *   scale_start_index [num_cams, num_scale]     absolute row   int32, device
+ *   sample_location   [bs, num_anchors, num_pts, num_cams, 2]  f32 (x, y) normalised
+ *   weights           [bs, num_anchors, num_pts, num_cams, num_scale, num_groups]  f32
+ *   output            [bs, num_anchors, num_embeds]            f32
+ *
+ * Differences from the reference launchers, all deliberate:
+ *   - outputs are fully written by the kernels: they need NOT be pre-zeroed
+ *     (the reference accumulates with atomicAdd into at::zeros buffers);
+ *   - results are deterministic (no floating-point atomics anywhere);
+ *   - 64-bit offsets: bs*num_pts*num_embeds*num_anchors*num_cams*num_scale may exceed 2^31.
+ */
+#ifndef HIPAD_DFA_H_
+#define HIPAD_DFA_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HIPAD_DFA_VERSION 1
+
+/* negative status codes (positive values are cudaError_t) */
+#define HIPAD_DFA_ERR_BAD_ARGUMENT   (-1)  /* null pointer, non-positive dim, num_embeds % num_groups != 0 */
+#define HIPAD_DFA_ERR_UNSUPPORTED    (-2)  /* shape outside the compiled kernel family */
+#define HIPAD_DFA_ERR_WORKSPACE      (-3)  /* workspace pointer null / too small / misaligned */
+
+int hipad_dfa_version(void);
+const char *hipad_dfa_error_string(int status);
+
+/* ---- forward: replaces deformable_aggregation() (deformable_aggregation_cuda.cu:265-288) ---- */
+int hipad_dfa_forward_f32(float *output, const float *mc_ms_feat,
+                          const int32_t *spatial_shape, const int32_t *scale_start_index,
+                          const float *sample_location, const float *weights,
+                          int batch_size, int num_cams, int num_feat, int num_embeds,
+                          int num_scale, int num_anchors, int num_pts, int num_groups,
+                          void *stream);
+
+/* same, feature maps stored as bf16 (raw uint16 bits); fp32 accumulation, fp32 output */
+int hipad_dfa_forward_bf16(float *output, const uint16_t *mc_ms_feat,
+                           const int32_t *spatial_shape, const int32_t *scale_start_index,
+                           const float *sample_location, const float *weights,
+                           int batch_size, int num_cams, int num_feat, int num_embeds,
+                           int num_scale, int num_anchors, int num_pts, int num_groups,
+                           void *stream);
+
+/* ---- backward: replaces deformable_aggregation_grad() (deformable_aggregation_cuda.cu:291-318) ----
+ * Bytes of scratch the backward needs (sorted sample records + segment table).  Pure host
+ * arithmetic on the sizes; the result is an upper bound valid for any spatial_shape whose
+ * rows sum to num_feat. */
+size_t hipad_dfa_backward_workspace_bytes(int batch_size, int num_cams, int num_feat,
+                                          int num_embeds, int num_scale, int num_anchors,
+                                          int num_pts, int num_groups);
+
+/* Writes ALL of grad_mc_ms_feat [bs,num_feat,C], grad_sampling_location and grad_weights
+ * (zeros where nothing contributes).  grad_mc_ms_feat may be NULL: the feature-gradient pass is
+ * then skipped (frozen backbone).  workspace: device memory, 256-byte aligned, at least
+ * hipad_dfa_backward_workspace_bytes(...) bytes, private to this call until it completes. */
+int hipad_dfa_backward_f32(const float *mc_ms_feat,
+                           const int32_t *spatial_shape, const int32_t *scale_start_index,
+                           const float *sample_location, const float *weights,
+                           const float *grad_output,
+                           float *grad_mc_ms_feat, float *grad_sampling_location, float *grad_weights,
+                           int batch_size, int num_cams, int num_feat, int num_embeds,
+                           int num_scale, int num_anchors, int num_pts, int num_groups,
+                           void *workspace, size_t workspace_bytes, void *stream);
+
+/* bf16 feature maps; grad_mc_ms_feat is written as bf16 (fp32 accumulation, one rounding) */
+int hipad_dfa_backward_bf16(const uint16_t *mc_ms_feat,
+                            const int32_t *spatial_shape, const int32_t *scale_start_index,
+                            const float *sample_location, const float *weights,
+                            const float *grad_output,
+                            uint16_t *grad_mc_ms_feat, float *grad_sampling_location, float *grad_weights,
+                            int batch_size, int num_cams, int num_feat, int num_embeds,
+                            int num_scale, int num_anchors, int num_pts, int num_groups,
+                            void *workspace, size_t workspace_bytes, void *stream);
+
+/* ---- integer sampling contract (parity instrument) ----
+ * indices: int32 [bs, A, P, cams, L, 6] = {valid, h_low, w_low, level_offset, corner_mask, row0},
+ * computed by the SAME device routine the kernels above use
+ * (mirrors deformable_aggregation_cuda.cu:166-181 and :19-53). */
+int hipad_dfa_sample_indices(int32_t *indices,
+                             const int32_t *spatial_shape, const int32_t *scale_start_index,
+                             const float *sample_location,
+                             int batch_size, int num_cams, int num_scale, int num_anchors, int num_pts,
+                             void *stream);
+
+/* ---- fused module forward (inference): projection + group softmax + aggregation ----
+ * Replaces, in one launch sequence, the chain of
+ *   DeformableFeatureAggregation.project_points   (models/blocks.py:217-225)
+ *   softmax over cams*L*P per group               (models/blocks.py:196-208)
+ *   the two permute/contiguous copies             (models/blocks.py:138-158)
+ *   deformable_aggregation()                      (deformable_aggregation_cuda.cu:265-288)
+ *   key_points      [bs, A, P, 3]                 f32
+ *   projection_mat  [bs, cams, 4, 4]              f32
+ *   image_wh        [bs, cams, 2] or NULL         f32
+ *   logits          [bs, A, cams, L, P, G]        f32, raw weights_fc output (pre-softmax)
+ * Optional outputs (may be NULL): sample_location_out [bs,A,P,cams,2] as consumed by the sampler. */
+int hipad_dfa_fused_forward_f32(float *output, const float *mc_ms_feat,
+                                const int32_t *spatial_shape, const int32_t *scale_start_index,
+                                const float *key_points, const float *projection_mat,
+                                const float *image_wh, const float *logits,
+                                float *sample_location_out,
+                                int batch_size, int num_cams, int num_feat, int num_embeds,
+                                int num_scale, int num_anchors, int num_pts, int num_groups,
+                                void *stream);
+
+int hipad_dfa_fused_forward_bf16(float *output, const uint16_t *mc_ms_feat,
+                                 const int32_t *spatial_shape, const int32_t *scale_start_index,
+                                 const float *key_points, const float *projection_mat,
+                                 const float *image_wh, const float *logits,
+                                 float *sample_location_out,
+                                 int batch_size, int num_cams, int num_feat, int num_embeds,
+                                 int num_scale, int num_anchors, int num_pts, int num_groups,
+                                 void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HIPAD_DFA_H_ */
