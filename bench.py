@@ -1,0 +1,509 @@
+#!/usr/bin/env python
+"""bench.py — deformable-aggregation fwd+bwd throughput on B200 (BASELINE.json metric).
+
+One "step" = one pass of the hot path over one batch of synthetic input: every deformable
+aggregation call of a HiP-AD stage-2 decoder (6 layers x {det 900x13, map 100x300, plan 480x90,
+ego 1x13}; 6 cameras, 4 FPN levels of a 352x640 input, 256 channels, 8 groups), forward AND
+backward, on `--bs` samples per GPU.  N GPUs = N batch shards, no data-path collective (weak
+scaling).
+
+  value     algorithmic GB/s (SURVEY.md §8d byte counts) with every input already in HBM, the
+            step issued through the C ABI and replayed as one CUDA graph
+  e2e       same step through the public Python API (hipad_b200.deformable_aggregation_function
+            + autograd) from pinned HOST buffers, H2D/D2H inside the timed region
+  roofline  dominant kernel: algorithmic bytes per launch / CUDA-event duration vs measured HBM peak
+  cpu_baseline / --impl reference: the reference's own CPU path (torch grid_sample branch,
+            oracle/torch_path.py restatement) on the host cores, bounded sample
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+MODALITIES = (("det", 900, 13), ("map", 100, 300), ("plan", 480, 90), ("ego", 1, 13))
+LAYERS = 6
+FINAL_HW = (352, 640)
+C, G, CAMS = 256, 8, 6
+METRIC = "deform-agg fwd+bwd GB/s"
+
+
+def level_hw(final_hw):
+    return [(final_hw[0] // s, final_hw[1] // s) for s in (4, 8, 16, 32)]
+
+
+# ------------------------------------------------------------------------------------- inputs
+def make_calls(bs, seed, layers=LAYERS, modalities=MODALITIES):
+    """numpy inputs of every DFA call of one step (locations/weights differ per layer and modality)."""
+    import helpers as H
+    calls = []
+    for layer in range(layers):
+        for mi, (kind, A, P) in enumerate(modalities):
+            geo_kind = "det" if kind == "ego" else kind
+            c = H.make_geo_case(seed * 1000 + layer * 10 + mi, geo_kind, bs, level_hw(FINAL_HW), FINAL_HW,
+                                C=C, G=G, A=A, P=P, with_feat=False)
+            if kind == "ego":
+                # ego key points sit inside the ego box: visible to no camera (measured 0.000)
+                c["loc"] = np.full_like(c["loc"], -1.0) + 0.1 * np.random.default_rng(seed + layer).random(
+                    c["loc"].shape, dtype=np.float32)
+            rng = np.random.default_rng(seed * 77 + layer * 10 + mi)
+            calls.append(dict(kind=kind, layer=layer, A=A, P=P, loc=c["loc"], weights=c["weights"],
+                              grad_out=rng.standard_normal((bs, A, C), dtype=np.float32)))
+    import helpers
+    shapes, starts, F = helpers.level_tables(level_hw(FINAL_HW), CAMS)
+    return calls, shapes, starts, F
+
+
+def algorithmic_bytes(ops, shapes_d, starts_d, loc_d, bs, F, A, P, L, elem_bytes):
+    """B_fwd, B_bwd with U = distinct feature rows touched (counted on the GPU from
+    the kernels' own integer indices)."""
+    idx = ops.sample_indices(shapes_d, starts_d, loc_d)            # [bs,A,P,cams,L,6]
+    valid = idx[..., 0] > 0
+    row0 = idx[..., 5].long()
+    w = shapes_d[:, :, 1].long()[None, None, None]                 # [1,1,1,cams,L]
+    mask = idx[..., 4]
+    rows = []
+    for k, off in enumerate((0, 1, w, w + 1)):
+        ok = valid & ((mask >> k) & 1).bool()
+        r = row0 + off + (torch.arange(bs, device=idx.device) * F)[:, None, None, None, None]
+        rows.append(r[ok])
+    U = int(torch.unique(torch.cat(rows)).numel()) if rows else 0
+    n_valid = int(valid[..., 0].sum())
+    loc_b = bs * A * P * CAMS * 2 * 4
+    w_b = bs * A * P * CAMS * L * G * 4
+    out_b = bs * A * C * 4
+    feat_b = U * C * elem_bytes
+    b_fwd = loc_b + w_b + feat_b + out_b
+    b_bwd = out_b + loc_b + w_b + feat_b + w_b + loc_b + bs * F * C * elem_bytes
+    return dict(U=U, n_valid=n_valid, fwd=b_fwd, bwd=b_bwd, dense_gfeat=bs * F * C * elem_bytes,
+                bwd_sample=b_bwd - bs * F * C * elem_bytes)
+
+
+# ------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.QUERY, "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------- GPU arm
+def gpu_arm(args):
+    import torch.distributed as dist
+    import hipad_b200
+    from hipad_b200 import _lib
+    ops = hipad_b200.ops
+    lib = _lib.get()   # raises if the CUDA library is missing: there is no fallback
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a GPU (use --impl reference for the CPU arm)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    bf16 = args.dtype == "bf16"
+    elem = 2 if bf16 else 4
+    bs = args.bs
+    L = 4
+
+    calls, shapes, starts, F = make_calls(bs, seed=rank)
+    rng = np.random.default_rng(1234 + rank)
+    feat_h = torch.from_numpy(rng.standard_normal((bs, F, C), dtype=np.float32))
+    if bf16:
+        feat_h = feat_h.bfloat16()
+    feat = feat_h.to(dev)
+    shapes_d = torch.from_numpy(shapes).to(dev)
+    starts_d = torch.from_numpy(starts).to(dev)
+    dims = lambda c: (bs, CAMS, F, C, L, c["A"], c["P"], G)
+    ws_bytes = max(lib.hipad_dfa_backward_workspace_bytes(*dims(c)) for c in calls)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    g_feat = torch.empty_like(feat)   # one buffer reused by every call of the step (written in full each time)
+    total_fwd = total_bwd = 0
+    for c in calls:
+        c["loc_d"] = torch.from_numpy(c["loc"]).to(dev)
+        c["w_d"] = torch.from_numpy(c["weights"]).to(dev)
+        c["go_d"] = torch.from_numpy(c["grad_out"]).to(dev)
+        c["out_d"] = torch.empty((bs, c["A"], C), dtype=torch.float32, device=dev)
+        c["g_loc_d"] = torch.empty_like(c["loc_d"])
+        c["g_w_d"] = torch.empty_like(c["w_d"])
+        c["bytes"] = algorithmic_bytes(ops, shapes_d, starts_d, c["loc_d"], bs, F, c["A"], c["P"], L, elem)
+        total_fwd += c["bytes"]["fwd"]
+        total_bwd += c["bytes"]["bwd"]
+    step_bytes = total_fwd + total_bwd
+
+    fwd_fn = lib.hipad_dfa_forward_bf16 if bf16 else lib.hipad_dfa_forward_f32
+
+    def fwd_call(c, stream):
+        _lib.check(fwd_fn(c["out_d"].data_ptr(), feat.data_ptr(), shapes_d.data_ptr(), starts_d.data_ptr(),
+                          c["loc_d"].data_ptr(), c["w_d"].data_ptr(), *dims(c), stream), "forward")
+
+    def bwd_call(c, stream, mask=7):
+        _lib.check(lib.hipad_dfa_backward_stages(
+            1 if bf16 else 0, mask, feat.data_ptr(), shapes_d.data_ptr(), starts_d.data_ptr(),
+            c["loc_d"].data_ptr(), c["w_d"].data_ptr(), c["go_d"].data_ptr(), g_feat.data_ptr(),
+            c["g_loc_d"].data_ptr(), c["g_w_d"].data_ptr(), *dims(c), ws.data_ptr(), ws_bytes, stream), "backward")
+
+    def issue_step(stream):
+        for c in calls:                 # decoder forward: 6 layers x 4 modalities
+            fwd_call(c, stream)
+        for c in reversed(calls):       # autograd order
+            bwd_call(c, stream)
+
+    launches_per_step = len(calls) * (1 + 4)
+    flush = torch.zeros(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
+
+    def flush_l2():
+        # read-only sweep of 256 MiB: evicts everything, leaves only clean lines behind
+        return flush.view(torch.int64).sum()
+
+    # ---- capture one step as a CUDA graph (launch-bound at bs=1 otherwise)
+    stream = torch.cuda.Stream(device=dev)
+    graph = None
+    with torch.cuda.stream(stream):
+        issue_step(stream.cuda_stream)
+        stream.synchronize()
+        if not args.no_graph:
+            try:
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph, stream=stream):
+                    issue_step(torch.cuda.current_stream().cuda_stream)
+            except Exception as e:  # keep measuring, eagerly
+                print("graph capture failed, timing eager launches:", e, file=sys.stderr)
+                graph = None
+    torch.cuda.synchronize()
+
+    def run_step():
+        if graph is not None:
+            graph.replay()
+        else:
+            issue_step(torch.cuda.current_stream().cuda_stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with torch.cuda.stream(stream):
+        for _ in range(max(args.warmup, 3)):
+            flush_l2()
+            run_step()
+        barrier()
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        barrier()
+        for a, b in ev:
+            flush_l2()                  # L2 flush between timed iterations (outside the timed interval)
+            a.record()
+            run_step()
+            b.record()
+        barrier()
+        step_ms = [a.elapsed_time(b) for a, b in ev]
+        clocks = sampler.stop() if rank == 0 else None
+    total_ms = float(sum(step_ms))
+    t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    ms_per_step = total_ms / args.steps
+    value = world * step_bytes / (ms_per_step * 1e-3) / 1e9
+
+    # ---- per-kernel timing (CUDA events on the launching stream), for the roofline object
+    kern = {"dfa_sample_kernel<fwd>": [], "dfa_sample_kernel<bwd>": [], "dfa_bucket_sort_kernel": [],
+            "dfa_gfeat_reduce_kernel": []}
+    kbytes = {k: [] for k in kern}
+    per_mod = {}
+    with torch.cuda.stream(stream):
+        s = stream.cuda_stream
+        for rep in range(3):
+            flush_l2()
+            for c in calls:
+                e = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+                e[0].record(); fwd_call(c, s); e[1].record()
+                bwd_call(c, s, 1); e[2].record()
+                bwd_call(c, s, 2); e[3].record()
+                bwd_call(c, s, 4); e[4].record()
+                c["_ev"] = e
+            stream.synchronize()
+            if rep == 0:
+                continue
+            for c in calls:
+                e = c["_ev"]
+                d = [e[i].elapsed_time(e[i + 1]) * 1e3 for i in range(4)]   # microseconds
+                for name, dur, nb in zip(kern, d, (c["bytes"]["fwd"], c["bytes"]["bwd_sample"], 0,
+                                                   c["bytes"]["dense_gfeat"])):
+                    kern[name].append(dur)
+                    kbytes[name].append(nb)
+                m = per_mod.setdefault(c["kind"], dict(fwd_us=[], bwd_us=[], bytes=c["bytes"]))
+                m["fwd_us"].append(d[0]); m["bwd_us"].append(d[1] + d[2] + d[3])
+    share = {k: float(np.sum(v)) for k, v in kern.items()}
+    dominant = max(share, key=share.get)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "6650 GB/s (of fallback)"
+    dom_us = float(np.mean(kern[dominant]))
+    dom_bytes = float(np.mean(kbytes[dominant]))
+    achieved = dom_bytes / (dom_us * 1e-6) / 1e9
+    traffic = None
+    try:   # dram bytes per launch of the dominant kernel from the committed ncu capture, if any
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json"))).get(dominant)
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "kernel": dominant, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
+                "avg_launch_us": round(dom_us, 2), "algorithmic_bytes_per_launch": int(dom_bytes),
+                "kernel_share_of_step": {k: round(v / max(sum(share.values()), 1e-9), 3) for k, v in share.items()},
+                "step_frac_of_peak": round(value / world / peak, 4)}
+
+    # ---- reference CUDA op (oracle/_ref, rebuilt from the reference sources) on the same inputs
+    ref_cuda = None
+    if not bf16:
+        try:
+            from oracle import build_ref
+            if build_ref.available():
+                ext = build_ref.load()
+                rf = feat
+                res = {}
+                for c in calls[:4]:
+                    z = lambda x: torch.zeros_like(x)
+                    for _ in range(2):
+                        ext.deformable_aggregation_forward(rf, shapes_d, starts_d, c["loc_d"], c["w_d"])
+                    torch.cuda.synchronize()
+                    e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+                    n = 5
+                    e0.record()
+                    for _ in range(n):
+                        ext.deformable_aggregation_forward(rf, shapes_d, starts_d, c["loc_d"], c["w_d"])
+                    e1.record()
+                    for _ in range(n):
+                        gf, gl, gw = z(rf), z(c["loc_d"]), z(c["w_d"])
+                        ext.deformable_aggregation_backward(rf, shapes_d, starts_d, c["loc_d"], c["w_d"], c["go_d"],
+                                                            gf, gl, gw)
+                    e2.record()
+                    torch.cuda.synchronize()
+                    res[c["kind"]] = {"ref_fwd_us": round(e0.elapsed_time(e1) * 1e3 / n, 1),
+                                      "ref_bwd_us": round(e1.elapsed_time(e2) * 1e3 / n, 1),
+                                      "ours_fwd_us": round(float(np.mean(per_mod[c["kind"]]["fwd_us"])), 1),
+                                      "ours_bwd_us": round(float(np.mean(per_mod[c["kind"]]["bwd_us"])), 1)}
+                ref_cuda = res
+        except Exception as e:
+            ref_cuda = {"error": str(e)[:200]}
+
+    # ---- end to end through the public Python API, host buffers, H2D + D2H inside the timed region
+    e2e = None
+    if not args.skip_e2e:
+        pin = lambda x: torch.from_numpy(x).pin_memory()
+        host = [dict(loc=pin(c["loc"]), w=pin(c["weights"]), go=pin(c["grad_out"])) for c in calls]
+        feat_pin = feat_h.pin_memory()
+        h2d = feat_pin.numel() * feat_pin.element_size() + sum(
+            h["loc"].numel() * 4 + h["w"].numel() * 4 + h["go"].numel() * 4 for h in host)
+        out_host = [torch.empty((bs, c["A"], C), dtype=torch.float32).pin_memory() for c in calls]
+        gsum_host = torch.empty(3, dtype=torch.float32).pin_memory()
+        d2h = sum(o.numel() * 4 for o in out_host) + 12
+
+        def e2e_step():
+            f = feat_pin.to(dev, non_blocking=True).requires_grad_(True)
+            sh, st = shapes_d, starts_d
+            outs, leaves = [], []
+            for c, h in zip(calls, host):
+                loc = h["loc"].to(dev, non_blocking=True).requires_grad_(True)
+                w = h["w"].to(dev, non_blocking=True).requires_grad_(True)
+                outs.append(hipad_b200.deformable_aggregation_function(f, sh, st, loc, w))
+                leaves.append((loc, w))
+            gos = [h["go"].to(dev, non_blocking=True) for h in host]
+            torch.autograd.backward(outs, gos)
+            for o, oh in zip(outs, out_host):
+                oh.copy_(o.detach(), non_blocking=True)
+            gsum_host.copy_(torch.stack([f.grad.float().abs().sum(), leaves[0][0].grad.abs().sum(),
+                                         leaves[0][1].grad.abs().sum()]), non_blocking=True)
+
+        n_e2e = max(2, min(args.steps, 5))
+        e2e_step(); torch.cuda.synchronize()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            e2e_step()
+        torch.cuda.synchronize()
+        dt = torch.tensor([(time.perf_counter() - t0) / n_e2e], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        e2e = {"value": round(world * step_bytes / float(dt.item()) / 1e9, 2), "unit": "GB/s",
+               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+               "ms_per_step": round(float(dt.item()) * 1e3, 3), "steps": n_e2e,
+               "api": "hipad_b200.deformable_aggregation_function + autograd, pinned host buffers"}
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.skip_cpu:
+        cpu_baseline = cpu_reference(budget_s=args.cpu_budget, steps=None, warmup=1)["cpu_baseline"]
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": round(value, 2), "unit": "GB/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": round(ms_per_step, 4), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if bf16 else "f32", "data": "synthetic",
+            "config": {"workload": "HiP-AD stage-2 decoder DFA path: 6 layers x (det 900x13 + map 100x300 + "
+                                   "plan 480x90 + ego 1x13), 6 cams, 4 levels of 352x640, C=256, G=8, fwd+bwd",
+                       "bs_per_gpu": bs, "feature_dtype": args.dtype, "parallelism": "batch-sharded x%d" % world,
+                       "l2": "256 MiB read sweep (flush) between timed steps", "cuda_graph": graph is not None,
+                       "locations": "B2D camera geometry, det/map/plan visible fraction ~0.20/0.19/0.13, ego 0"},
+            "samples_per_s": round(world * bs / (ms_per_step * 1e-3), 2),
+            "algorithmic_bytes_per_step": int(step_bytes),
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
+            "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "per_call_us": {k: {"fwd": round(float(np.mean(v["fwd_us"])), 1), "bwd": round(float(np.mean(v["bwd_us"])), 1),
+                                "B_fwd": v["bytes"]["fwd"], "B_bwd": v["bytes"]["bwd"], "U_rows": v["bytes"]["U"]}
+                            for k, v in per_mod.items()},
+            "kernel_avg_us": {k: round(float(np.mean(v)), 2) for k, v in kern.items()},
+            "reference_cuda_op_same_gpu": ref_cuda,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------- CPU arm
+def cpu_reference(budget_s, steps, warmup):
+    """The reference's CPU implementation of the path (torch grid_sample branch) on the host cores.
+
+    Sample: the four DFA calls of ONE decoder layer at bs=1 (1/6 of a GPU step); shrunk to the det
+    call alone if a layer would not fit the time budget."""
+    from oracle import torch_path as tp
+    import helpers as H
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    calls, shapes, starts, F = make_calls(1, seed=0, layers=1)
+    rng = np.random.default_rng(1234)
+    lv = level_hw(FINAL_HW)
+    fmaps = [torch.from_numpy(rng.standard_normal((1, CAMS, C, h, w), dtype=np.float32)).requires_grad_(True)
+             for h, w in lv]
+
+    def bytes_of(c):
+        # same definition as the GPU arm, U counted with the oracle's integer indices
+        import oracle
+        U = oracle.unique_rows(shapes, starts, c["loc"], F)
+        A, P = c["A"], c["P"]
+        loc_b, w_b, out_b = A * P * CAMS * 8, A * P * CAMS * 4 * G * 4, A * C * 4
+        return (loc_b + w_b + U * C * 4 + out_b) + (out_b + 2 * loc_b + 2 * w_b + U * C * 4 + F * C * 4)
+
+    def run(sample):
+        for c in sample:
+            p2d = torch.from_numpy(c["loc"]).permute(0, 3, 1, 2, 4).contiguous().requires_grad_(True)
+            w = torch.from_numpy(c["weights"]).permute(0, 1, 3, 4, 2, 5).contiguous().requires_grad_(True)
+            out = tp.grid_sample_path(fmaps, p2d, w)
+            out.backward(torch.from_numpy(c["grad_out"]))
+
+    sample, desc = calls, "one decoder layer (det+map+plan+ego calls), bs=1, fwd+bwd, torch grid_sample path"
+    t0 = time.perf_counter(); run(sample); first = time.perf_counter() - t0
+    n = steps if steps is not None else max(1, int(budget_s // max(first, 1e-3)))
+    if first * (n + warmup) > 170:
+        sample, desc = calls[:1], "det call only (900x13), bs=1, fwd+bwd, torch grid_sample path"
+        t0 = time.perf_counter(); run(sample); first = time.perf_counter() - t0
+    for _ in range(max(0, warmup - 1)):
+        run(sample)
+    times = []
+    for _ in range(n):
+        t0 = time.perf_counter(); run(sample); times.append(time.perf_counter() - t0)
+    nbytes = sum(bytes_of(c) for c in sample)
+    sec = float(np.mean(times))
+    val = nbytes / sec / 1e9
+    return {"value": val, "ms_per_step": sec * 1e3, "steps": n,
+            "cpu_baseline": {"value": round(val, 4), "unit": "GB/s", "cores": cores, "kind": "port",
+                             "sample": desc + "; %d timed runs, %.2f s each" % (n, sec)}}
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    r = cpu_reference(budget_s=args.cpu_budget, steps=args.steps, warmup=max(1, min(args.warmup, 2)))
+    line = {"impl": "reference", "metric": METRIC, "value": round(r["value"], 4), "unit": "GB/s",
+            "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": r["steps"], "warmup": max(1, min(args.warmup, 2)),
+            "ms_per_step": round(r["ms_per_step"], 2), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "HiP-AD stage-2 decoder DFA path (reference CPU torch path, bounded sample)",
+                       "bs_per_gpu": 1},
+            "cpu_baseline": r["cpu_baseline"],
+            "e2e": {"value": round(r["value"], 4), "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--bs", type=int, default=1, help="samples per GPU")
+    ap.add_argument("--dtype", default="f32", choices=["f32", "bf16"], help="feature-map storage type")
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--skip-e2e", action="store_true")
+    ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of CPU baseline work")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -260,7 +260,7 @@ class DeformableFeatureAggregation(nn.Module):
         if self.use_deformable_func:
             dropping = self.training and self.attn_drop > 0
             fusable = (self.fused_inference and not dropping and not torch.is_grad_enabled()
-                       and 128 % self.num_groups == 0)
+                       and 256 % self.num_groups == 0)
             if fusable:
                 logits = self._get_logits(instance_feature, anchor_embed, metas)
                 features = _ops.fused_deformable_aggregation(

@@ -44,7 +44,7 @@ int fused_common(ElemType t, float* output, const void* feat, const int32_t* sha
 int backward_common(ElemType t, const void* feat, const int32_t* shapes, const int32_t* starts, const float* loc,
                     const float* weights, const float* grad_output, void* g_feat, float* g_loc, float* g_w, int bs,
                     int cams, int num_feat, int C, int L, int A, int P, int G, void* workspace, size_t workspace_bytes,
-                    void* stream) {
+                    void* stream, int stage_mask = 7) {
     if (!feat || !shapes || !starts || !loc || !weights || !grad_output || !g_loc || !g_w ||
         bad_dims(bs, cams, num_feat, C, L, A, P, G))
         return HIPAD_DFA_ERR_BAD_ARGUMENT;
@@ -54,6 +54,7 @@ int backward_common(ElemType t, const void* feat, const int32_t* shapes, const i
     a.d = mk(bs, cams, num_feat, C, L, A, P, G);
     a.workspace = workspace; a.workspace_bytes = workspace_bytes;
     a.stream = reinterpret_cast<cudaStream_t>(stream);
+    a.stage_mask = stage_mask;
     return launch_backward(a);
 }
 }  // namespace
@@ -112,6 +113,18 @@ int hipad_dfa_backward_bf16(const uint16_t* mc_ms_feat, const int32_t* spatial_s
     return backward_common(kBF16, mc_ms_feat, spatial_shape, scale_start_index, sample_location, weights, grad_output,
                            grad_mc_ms_feat, grad_sampling_location, grad_weights, batch_size, num_cams, num_feat,
                            num_embeds, num_scale, num_anchors, num_pts, num_groups, workspace, workspace_bytes, stream);
+}
+
+int hipad_dfa_backward_stages(int feat_is_bf16, int stage_mask, const void* mc_ms_feat, const int32_t* spatial_shape,
+                              const int32_t* scale_start_index, const float* sample_location, const float* weights,
+                              const float* grad_output, void* grad_mc_ms_feat, float* grad_sampling_location,
+                              float* grad_weights, int batch_size, int num_cams, int num_feat, int num_embeds,
+                              int num_scale, int num_anchors, int num_pts, int num_groups, void* workspace,
+                              size_t workspace_bytes, void* stream) {
+    return backward_common(feat_is_bf16 ? kBF16 : kF32, mc_ms_feat, spatial_shape, scale_start_index, sample_location,
+                           weights, grad_output, grad_mc_ms_feat, grad_sampling_location, grad_weights, batch_size,
+                           num_cams, num_feat, num_embeds, num_scale, num_anchors, num_pts, num_groups, workspace,
+                           workspace_bytes, stream, stage_mask & 7);
 }
 
 int hipad_dfa_sample_indices(int32_t* indices, const int32_t* spatial_shape, const int32_t* scale_start_index,

@@ -9,7 +9,7 @@ constexpr size_t kAlign = 256;
 inline size_t align_up(size_t v) { return (v + kAlign - 1) / kAlign * kAlign; }
 
 struct WorkspaceLayout {
-    size_t rec, seg, counts, sortbuf, total;
+    size_t rec, seg, counts, sortbuf, heavy_list, heavy_count, total;
     int seg_stride;
 };
 
@@ -23,6 +23,8 @@ WorkspaceLayout workspace_layout(const Dims& d) {
     w.seg = off;     off += align_up((size_t)d.bs * w.seg_stride * sizeof(int));
     w.counts = off;  off += align_up((size_t)d.bs * n_cl * sizeof(int));
     w.sortbuf = off; off += align_up((size_t)d.bs * n_cl * 2 * AP * sizeof(unsigned long long));
+    w.heavy_list = off;  off += align_up((size_t)d.bs * d.num_feat * sizeof(int2));
+    w.heavy_count = off; off += align_up(sizeof(int));
     w.total = off;
     return w;
 }
@@ -33,6 +35,9 @@ int launch_reduce(const GfeatParams& gp, KernelShape ks, dim3 grid, cudaStream_t
 #define HIPAD_RED(V_, NCH_)                                                                \
     do {                                                                                   \
         dfa_gfeat_reduce_kernel<T, V_, NCH_><<<grid, kReduceWarps * 32, 0, st>>>(gp);      \
+        cudaError_t e_ = cudaGetLastError();                                               \
+        if (e_ != cudaSuccess) return (int)e_;                                             \
+        dfa_gfeat_heavy_kernel<T, V_, NCH_><<<kHeavyCtas, kReduceWarps * 32, 0, st>>>(gp); \
         return (int)cudaGetLastError();                                                    \
     } while (0)
     if (ks.vector) {
@@ -57,12 +62,13 @@ int launch_backward(const BwdArgs& a) {
                     (reinterpret_cast<uintptr_t>(a.grad_out) % 16 == 0) &&
                     (reinterpret_cast<uintptr_t>(a.g_w) % 16 == 0);
     const KernelShape ks = pick_shape(a.type, d.C, d.G, al);
-    if (!ks.ok || d.cams * d.L > kMaxCamLevels) return -2;
+    if (!ks.ok || d.cams * d.L > kMaxCamLevels || (long long)d.num_feat * d.C >= (1LL << 31)) return -2;
     const WorkspaceLayout wl = workspace_layout(d);
     if (a.workspace == nullptr || a.workspace_bytes < wl.total ||
         reinterpret_cast<uintptr_t>(a.workspace) % kAlign != 0)
         return -3;
     if ((long long)d.A * d.P > (1LL << 30)) return -2;
+    if ((long long)d.A * d.P * d.cams * d.L * d.G >= (1LL << 31) || (long long)d.A * d.C >= (1LL << 31)) return -2;
 
     // ---- K1: sample-major, g_w + g_loc (fully written)
     SampleParams p = {};
@@ -78,9 +84,12 @@ int launch_backward(const BwdArgs& a) {
     const long long grid = rows * p.S;
     if (grid > 0x7fffffffLL) return -2;
     const size_t smem = sample_smem_for(kBwd, d, ks, a.type, p.PS);
-    int rc = (a.type == kF32) ? dispatch_sample<float, kBwd, false>(p, ks, (int)grid, smem, a.stream)
-                              : dispatch_sample<__nv_bfloat16, kBwd, false>(p, ks, (int)grid, smem, a.stream);
-    if (rc != 0) return rc;
+    if (a.stage_mask & 1) {
+        const int rc = (a.type == kF32)
+                           ? dispatch_sample<float, kBwd, false>(p, ks, (int)grid, smem, a.stream)
+                           : dispatch_sample<__nv_bfloat16, kBwd, false>(p, ks, (int)grid, smem, a.stream);
+        if (rc != 0) return rc;
+    }
     if (a.g_feat == nullptr) return 0;   // caller does not need the feature-map gradient
 
     // ---- K2a: per-(b,cam,level) bucket sort of the visible samples by quad key
@@ -92,18 +101,23 @@ int launch_backward(const BwdArgs& a) {
     gp.seg = reinterpret_cast<int*>(ws + wl.seg);
     gp.counts = reinterpret_cast<int*>(ws + wl.counts);
     gp.sortbuf = reinterpret_cast<unsigned long long*>(ws + wl.sortbuf);
+    gp.heavy_list = reinterpret_cast<int2*>(ws + wl.heavy_list);
+    gp.heavy_count = reinterpret_cast<int*>(ws + wl.heavy_count);
     gp.d = d;
     gp.seg_stride = wl.seg_stride;
     const long long AP = (long long)d.A * d.P;
     int cap = 24576;
     if (AP < cap) cap = (int)((AP + 63) / 64 * 64);
     gp.smem_cap = cap;
-    const size_t sort_smem = bucket_sort_smem_bytes(cap);
-    cudaError_t e = ensure_smem(dfa_bucket_sort_kernel, sort_smem);
-    if (e != cudaSuccess) return (int)e;
-    dfa_bucket_sort_kernel<<<dim3((unsigned)(d.cams * d.L), (unsigned)d.bs), kSortThreads, sort_smem, a.stream>>>(gp);
-    e = cudaGetLastError();
-    if (e != cudaSuccess) return (int)e;
+    if (a.stage_mask & 2) {
+        const size_t sort_smem = bucket_sort_smem_bytes(cap);
+        cudaError_t e = ensure_smem(dfa_bucket_sort_kernel, sort_smem);
+        if (e != cudaSuccess) return (int)e;
+        dfa_bucket_sort_kernel<<<dim3((unsigned)(d.cams * d.L), (unsigned)d.bs), kSortThreads, sort_smem, a.stream>>>(gp);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return (int)e;
+    }
+    if (!(a.stage_mask & 4)) return 0;
 
     // ---- K2b: feature-major reduce, writes every row of g_feat once
     const unsigned tiles = (unsigned)((d.num_feat + kRowsPerTile - 1) / kRowsPerTile + d.cams * d.L);

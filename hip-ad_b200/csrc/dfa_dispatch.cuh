@@ -5,7 +5,7 @@
 
 namespace hipad {
 
-constexpr int kSampleWarps = 4;
+constexpr int kSampleWarps = 8;
 constexpr int kMaxPairsPerSlice = 8192;
 
 template <typename K>
@@ -58,7 +58,7 @@ int dispatch_sample(const SampleParams& p, KernelShape ks, int grid, size_t smem
 
 inline size_t sample_smem_for(int mode, const Dims& d, KernelShape ks, ElemType t, int ps) {
     const int V = ks.vector ? (t == kF32 ? 4 : 8) : 1;
-    return sample_smem_bytes<kSampleWarps>(mode, d.cams * d.L, ks.nch * 32 * V, ps, d.G, d.cams);
+    return (size_t)sample_smem_layout<kSampleWarps>(mode, d.cams * d.L, d.L, ks.nch * 32 * V, ps, d.G, d.cams).total;
 }
 
 }  // namespace hipad

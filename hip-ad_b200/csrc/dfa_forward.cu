@@ -35,7 +35,7 @@ int launch_forward(const FwdArgs& a) {
     const bool al = (reinterpret_cast<uintptr_t>(a.feat) % 16 == 0) &&
                     (reinterpret_cast<uintptr_t>(a.out) % 16 == 0);
     const KernelShape ks = pick_shape(a.type, d.C, d.G, al);
-    if (!ks.ok || d.cams * d.L > kMaxCamLevels) return -2;
+    if (!ks.ok || d.cams * d.L > kMaxCamLevels || (long long)d.num_feat * d.C >= (1LL << 31)) return -2;
     const int mode = a.fused ? kFused : kFwd;
     if (a.fused && ((kSampleWarps * 32) % d.G != 0)) return -2;
 

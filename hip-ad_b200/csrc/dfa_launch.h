@@ -54,6 +54,7 @@ struct BwdArgs {
     void* workspace;
     size_t workspace_bytes;
     cudaStream_t stream;
+    int stage_mask;   // bit0 sample-major (g_w,g_loc), bit1 bucket sort, bit2 feature-major reduce
 };
 int launch_backward(const BwdArgs& a);
 size_t backward_workspace_bytes(const Dims& d);

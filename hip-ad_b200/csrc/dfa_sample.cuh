@@ -68,19 +68,31 @@ __device__ __forceinline__ int block_compact_offset(bool flag, int* s_wcnt, int&
     return before + __popc(bal & ((1u << lane) - 1u));
 }
 
-// shared-memory carve-up (host mirrors this in sample_smem_bytes())
+// shared-memory carve-up, as byte OFFSETS from the dynamic-smem base (all multiples of 16) so the
+// compiler keeps every access in the shared address space (LDS/STS, 32-bit addressing).
+struct SampleSmem {
+    int tab, wcnt, red, part, lxy, lpair, mrows, mcoef, valid, gxy, proj, stat, red2, total;
+};
 template <int kWarps>
-__host__ __device__ inline size_t sample_smem_bytes(int mode, int n_cl, int cpad, int ps, int G, int cams) {
-    size_t b = 0;
-    b += (size_t)n_cl * 3 * sizeof(int);            // level table
-    b += 16 * sizeof(int);                          // warp counters
-    b = (b + 15) & ~(size_t)15;
-    b += (size_t)kWarps * cpad * sizeof(float);     // cross-warp reduction / group scratch
-    b += (size_t)cpad * sizeof(float);              // CTA partial row (cluster exchange)
-    b += (size_t)ps * (sizeof(float2) + sizeof(int));  // compacted list
-    if (mode == kBwd) b += ((size_t)ps + 15) & ~(size_t)15;  // validity bytes
-    if (mode == kFused) b += (size_t)(cams * 14 + 4 * G + 2 * kWarps * 32) * sizeof(float);
-    return (b + 15) & ~(size_t)15;
+__host__ __device__ inline SampleSmem sample_smem_layout(int mode, int n_cl, int L, int cpad, int ps, int G, int cams) {
+    SampleSmem o;
+    int b = 0;
+    auto take = [&](int bytes) { const int at = b; b += (bytes + 15) & ~15; return at; };
+    o.tab = take(n_cl * 3 * 4);
+    o.wcnt = take(16 * 4);
+    o.red = take(kWarps * cpad * 4);       // cross-warp reduction / group scratch
+    o.part = take(cpad * 4);               // CTA partial row (cluster exchange)
+    o.lxy = take(ps * 8);                  // compacted list: locations
+    o.lpair = take(ps * 4);                //                 pair ids
+    o.mrows = take(ps * L * 16);           // per (visible pair, level): 4 corner rows
+    o.mcoef = take(ps * L * 16);           //                            4 bilinear terms
+    o.valid = take(mode == kBwd ? ps : 0);
+    o.gxy = take(mode == kBwd ? ps * L * 8 : 0);   // per (pair, level) location-gradient partials
+    o.proj = take(mode == kFused ? cams * 14 * 4 : 0);
+    o.stat = take(mode == kFused ? 4 * G * 4 : 0);
+    o.red2 = take(mode == kFused ? 2 * kWarps * 32 * 4 : 0);
+    o.total = b;
+    return o;
 }
 
 template <typename T, int V, int NCH, int kL, int kMode, bool kShfl, bool kCluster, int kWarps>
@@ -96,23 +108,25 @@ __global__ void __launch_bounds__(kWarps * 32) dfa_sample_kernel(const SamplePar
     const int ba = blockIdx.x / p.S;
     const int slice = blockIdx.x - ba * p.S;
     const int b = ba / d.A;
-    const int pair_lo = slice * p.PS;
-    const int pair_hi = min(NP, pair_lo + p.PS);
+    // slice s owns pairs s, s+S, s+2S, ... (interleaved, so the S CTAs of a row see the same mix
+    // of cameras / key points and finish together)
+    const int n_mine = (NP - slice + p.S - 1) / p.S;
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    unsigned char* sp = smem_raw;
-    int* tab = reinterpret_cast<int*>(sp);            sp += (size_t)n_cl * 3 * sizeof(int);
-    int* s_wcnt = reinterpret_cast<int*>(sp);         sp += 16 * sizeof(int);
-    sp = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(sp) + 15) & ~(uintptr_t)15);
-    float* red = reinterpret_cast<float*>(sp);        sp += (size_t)kWarps * CPAD * sizeof(float);
-    float* part = reinterpret_cast<float*>(sp);       sp += (size_t)CPAD * sizeof(float);
-    float2* l_xy = reinterpret_cast<float2*>(sp);     sp += (size_t)p.PS * sizeof(float2);
-    int* l_pair = reinterpret_cast<int*>(sp);         sp += (size_t)p.PS * sizeof(int);
-    unsigned char* s_valid = sp;
-    if (kMode == kBwd) sp += ((size_t)p.PS + 15) & ~(size_t)15;
-    float* s_proj = reinterpret_cast<float*>(sp);     // kFused: cams*12 matrix rows 0..2, cams*2 wh
-    float* s_stat = s_proj + d.cams * 14;             // kFused: m[G], inv_s[G], scratch 2*G
-    float* s_red2 = s_stat + 4 * d.G;                 // kFused: per-thread (m,s)
+    const SampleSmem so = sample_smem_layout<kWarps>(kMode, n_cl, L, CPAD, p.PS, d.G, d.cams);
+    int* tab = reinterpret_cast<int*>(smem_raw + so.tab);
+    int* s_wcnt = reinterpret_cast<int*>(smem_raw + so.wcnt);
+    float* red = reinterpret_cast<float*>(smem_raw + so.red);
+    float* part = reinterpret_cast<float*>(smem_raw + so.part);
+    float2* l_xy = reinterpret_cast<float2*>(smem_raw + so.lxy);
+    int* l_pair = reinterpret_cast<int*>(smem_raw + so.lpair);
+    int4* m_rows = reinterpret_cast<int4*>(smem_raw + so.mrows);     // element rows of the 4 corners (clamped)
+    float4* m_coef = reinterpret_cast<float4*>(smem_raw + so.mcoef); // fwd: c1..c4   bwd: lh, lw, ok, (h<<16|w)
+    unsigned char* s_valid = smem_raw + so.valid;
+    float2* s_gxy = reinterpret_cast<float2*>(smem_raw + so.gxy);
+    float* s_proj = reinterpret_cast<float*>(smem_raw + so.proj);    // kFused: cams*12 matrix rows 0..2, cams*2 wh
+    float* s_stat = reinterpret_cast<float*>(smem_raw + so.stat);    // kFused: m[G], inv_s[G], scratch 2*G
+    float* s_red2 = reinterpret_cast<float*>(smem_raw + so.red2);    // kFused: per-thread (m,s)
 
     load_level_table(tab, p.shapes, p.starts, n_cl);
     if (kMode == kFused) {
@@ -125,11 +139,12 @@ __global__ void __launch_bounds__(kWarps * 32) dfa_sample_kernel(const SamplePar
 
     // ------------------------------------------------------------------ phase 1: visible pairs
     int n_list = 0;
-    for (int base = pair_lo; base < pair_hi; base += kThreads) {
-        const int pair = base + tid;
+    for (int base = 0; base < n_mine; base += kThreads) {
+        const int k_mine = base + tid;
+        const int pair = slice + k_mine * p.S;
         bool vis = false;
         float2 xy = make_float2(0.f, 0.f);
-        if (pair < pair_hi) {
+        if (k_mine < n_mine) {
             if (kMode == kFused) {
                 const int pt = pair / d.cams, cam = pair - pt * d.cams;
                 const float* kp = p.key_points + ((size_t)ba * d.P + pt) * 3;
@@ -152,7 +167,7 @@ __global__ void __launch_bounds__(kWarps * 32) dfa_sample_kernel(const SamplePar
             }
             vis = loc_valid(xy.x, xy.y);
             if (kMode == kBwd) {
-                s_valid[pair - pair_lo] = vis ? 1 : 0;
+                s_valid[k_mine] = vis ? 1 : 0;
                 if (!vis) reinterpret_cast<float2*>(p.g_loc)[(size_t)ba * NP + pair] = make_float2(0.f, 0.f);
             }
         }
@@ -169,15 +184,20 @@ __global__ void __launch_bounds__(kWarps * 32) dfa_sample_kernel(const SamplePar
     if (kMode == kBwd) {
         // zero the weight-gradient rows of invisible pairs (each row = L*G floats, contiguous)
         const int lg = L * d.G;
-        float* gw_base = p.g_w + ((size_t)ba * NP + pair_lo) * lg;
-        const int n_pairs = pair_hi - pair_lo;
+        float* gw_base = p.g_w + (size_t)ba * NP * lg;
         if ((lg & 3) == 0) {
             const int q_per = lg >> 2;
-            for (int q = tid; q < n_pairs * q_per; q += kThreads)
-                if (!s_valid[q / q_per]) reinterpret_cast<float4*>(gw_base)[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int q = tid; q < n_mine * q_per; q += kThreads) {
+                const int k_mine = q / q_per;
+                if (!s_valid[k_mine])
+                    reinterpret_cast<float4*>(gw_base)[(size_t)(slice + k_mine * p.S) * q_per + (q - k_mine * q_per)] =
+                        make_float4(0.f, 0.f, 0.f, 0.f);
+            }
         } else {
-            for (int q = tid; q < n_pairs * lg; q += kThreads)
-                if (!s_valid[q / lg]) gw_base[q] = 0.f;
+            for (int q = tid; q < n_mine * lg; q += kThreads) {
+                const int k_mine = q / lg;
+                if (!s_valid[k_mine]) gw_base[(size_t)(slice + k_mine * p.S) * lg + (q - k_mine * lg)] = 0.f;
+            }
         }
     }
 
@@ -243,14 +263,49 @@ __global__ void __launch_bounds__(kWarps * 32) dfa_sample_kernel(const SamplePar
         __syncthreads();
     }
 
+    // ------------------------------------------------------------------ phase 1b: gather metadata
+    // One thread per (visible pair, level) turns the location into corner rows and bilinear terms
+    // ONCE, instead of all 32 lanes of the consuming warp redoing the same scalar math.  Rows of
+    // out-of-bounds corners are redirected to an in-bounds corner of the SAME quad and their
+    // coefficient is zeroed, so phase 2 can issue its loads unconditionally (a valid sample always
+    // has at least one in-bounds corner; reading a corner the quad reads anyway keeps NaN/Inf
+    // behaviour identical to skipping the load).
+    for (int it = tid; it < n_list * L; it += kThreads) {
+        const int i = it / L, l = it - i * L;
+        const float2 xy = l_xy[i];
+        const int pair = l_pair[i];
+        const int cam = pair - (pair / d.cams) * d.cams;
+        const int* t = tab + (cam * L + l) * 3;
+        const int h = t[0], w = t[1];
+        const Quad q = quad_setup(xy.x, xy.y, h, w);
+        const int r1 = t[2] + q.h_low * w + q.w_low, r2 = r1 + 1, r3 = r1 + w, r4 = r3 + 1;
+        const int safe = q.ok1 ? r1 : (q.ok2 ? r2 : (q.ok3 ? r3 : r4));
+        m_rows[it] = make_int4(q.ok1 ? r1 : safe, q.ok2 ? r2 : safe, q.ok3 ? r3 : safe, q.ok4 ? r4 : safe);
+        if (kMode != kBwd) {
+            m_coef[it] = make_float4(q.ok1 ? q.hh * q.hw : 0.f, q.ok2 ? q.hh * q.lw : 0.f,
+                                     q.ok3 ? q.lh * q.hw : 0.f, q.ok4 ? q.lh * q.lw : 0.f);
+        } else {
+            const int ok = (int)q.ok1 | ((int)q.ok2 << 1) | ((int)q.ok3 << 2) | ((int)q.ok4 << 3);
+            m_coef[it] = make_float4(q.lh, q.lw, __int_as_float(ok), __int_as_float((h << 16) | w));
+        }
+    }
+    __syncthreads();
+
     // ------------------------------------------------------------------ phase 2: gather
+    // Work item = one (visible pair, level): 4 corner rows x NCH vector loads per lane.  Items are
+    // dealt round-robin to the warps of the CTA (fine-grained: an anchor's serial chain per warp is
+    // n_items / kWarps) and software-pipelined two deep: the loads of item n+1 are in flight while
+    // item n is consumed, i.e. 2 x 4 x NCH 16-byte loads outstanding per lane.
+    // Lanes whose channels fall beyond C (C < NCH*32*V) are clamped onto the last valid vector:
+    // they load real data and compute values nobody reads, which keeps the loop branch-free.
     int ch[NCH], grp[NCH];
     bool act[NCH];
 #pragma unroll
     for (int j = 0; j < NCH; ++j) {
-        ch[j] = (j * 32 + lane) * V;
-        act[j] = ch[j] < d.C;
-        grp[j] = act[j] ? ch[j] / gd : 0;
+        const int c_raw = (j * 32 + lane) * V;
+        act[j] = c_raw < d.C;
+        ch[j] = act[j] ? c_raw : d.C - V;
+        grp[j] = ch[j] / gd;
         if (kMode == kFused) {
             sm_m[j] = s_stat[grp[j]];
             sm_inv[j] = s_stat[d.G + grp[j]];
@@ -267,103 +322,147 @@ __global__ void __launch_bounds__(kWarps * 32) dfa_sample_kernel(const SamplePar
     if (kMode == kBwd) {
 #pragma unroll
         for (int j = 0; j < NCH; ++j)
-            if (act[j]) VecIO<float, V>::load(p.grad_out + (size_t)ba * d.C + ch[j], go[j]);
+            if (act[j]) VecIO<float, V>::load(p.grad_out + (size_t)ba * d.C + ch[j], go[j]);   // inactive: stays 0
     }
 
-    const T* feat = reinterpret_cast<const T*>(p.feat);
-    const size_t feat_b = (size_t)b * d.num_feat;
+    // element offsets inside one batch element fit 32 bits (num_feat*C < 2^31, checked on the host)
+    const T* featb = reinterpret_cast<const T*>(p.feat) + (size_t)b * d.num_feat * d.C;
+    const unsigned Cu = (unsigned)d.C;
+    const int n_items = n_list * L;
 
-    for (int i = warp; i < n_list; i += kWarps) {
-        const float2 xy = l_xy[i];
-        const int pair = l_pair[i];
-        const int pt = pair / d.cams, cam = pair - pt * d.cams;
-        const int* t = tab + cam * L * 3;
+    struct Item {
+        float v[4][NCH][V];
+        float wv[NCH];
+        float4 cf;
+        int pair, l;
+    };
+
+    auto issue = [&](int it, Item& r) {
+        const int i = it / L;
+        r.l = it - i * L;
+        r.pair = l_pair[i];
+        const int4 rw = m_rows[it];
+        r.cf = m_coef[it];
+        const int pt = r.pair / d.cams, cam = r.pair - pt * d.cams;
         const float* wrow = (kMode == kFused)
-                                ? p.weights + ((size_t)ba * d.cams + cam) * L * d.P * d.G + (size_t)pt * d.G
-                                : p.weights + ((size_t)ba * NP + pair) * L * d.G;
-        float gx = 0.f, gy = 0.f;
+                                ? p.weights + (((size_t)ba * d.cams + cam) * L + r.l) * d.P * d.G + (size_t)pt * d.G
+                                : p.weights + (((size_t)ba * NP + r.pair) * L + r.l) * d.G;
 #pragma unroll
-        for (int l = 0; l < L; ++l) {
-            const int h = t[l * 3], w = t[l * 3 + 1];
-            const Quad q = quad_setup(xy.x, xy.y, h, w);
-            const T* r1 = feat + (feat_b + t[l * 3 + 2] + (ptrdiff_t)q.h_low * w + q.w_low) * d.C;
-            const T* r3 = r1 + (size_t)w * d.C;
-            const float c1 = q.hh * q.hw, c2 = q.hh * q.lw, c3 = q.lh * q.hw, c4 = q.lh * q.lw;
-            float wv[NCH];
+        for (int j = 0; j < NCH; ++j) r.wv[j] = __ldg(wrow + grp[j]);
+        // one 64-bit row pointer per corner; the NCH chunks are constant offsets from it
+        const T* q1 = featb + (size_t)((unsigned)rw.x * Cu);
+        const T* q2 = featb + (size_t)((unsigned)rw.y * Cu);
+        const T* q3 = featb + (size_t)((unsigned)rw.z * Cu);
+        const T* q4 = featb + (size_t)((unsigned)rw.w * Cu);
 #pragma unroll
-            for (int j = 0; j < NCH; ++j) {
-                if (kMode == kFused) {
-                    const float x = act[j] ? __ldg(wrow + (size_t)l * d.P * d.G + grp[j]) : 0.f;
-                    wv[j] = expf(x - sm_m[j]) * sm_inv[j];
-                } else {
-                    wv[j] = act[j] ? __ldg(wrow + l * d.G + grp[j]) : 0.f;
-                }
-            }
-            float v1[NCH][V], v2[NCH][V], v3[NCH][V], v4[NCH][V];
-#pragma unroll
-            for (int j = 0; j < NCH; ++j) {
-#pragma unroll
-                for (int e = 0; e < V; ++e) { v1[j][e] = 0.f; v2[j][e] = 0.f; v3[j][e] = 0.f; v4[j][e] = 0.f; }
-                if (act[j]) {
-                    if (q.ok1) VecIO<T, V>::load(r1 + ch[j], v1[j]);
-                    if (q.ok2) VecIO<T, V>::load(r1 + d.C + ch[j], v2[j]);
-                    if (q.ok3) VecIO<T, V>::load(r3 + ch[j], v3[j]);
-                    if (q.ok4) VecIO<T, V>::load(r3 + d.C + ch[j], v4[j]);
-                }
-            }
-            if (kMode != kBwd) {
-#pragma unroll
-                for (int j = 0; j < NCH; ++j)
-#pragma unroll
-                    for (int e = 0; e < V; ++e) {
-                        const float val = c1 * v1[j][e] + c2 * v2[j][e] + c3 * v3[j][e] + c4 * v4[j][e];
-                        acc[j][e] = __fmaf_rn(val, wv[j], acc[j][e]);
-                    }
-            } else {
-                float gxl = 0.f, gyl = 0.f;
-#pragma unroll
-                for (int j = 0; j < NCH; ++j) {
-                    float gw = 0.f, dxs = 0.f, dys = 0.f;
-#pragma unroll
-                    for (int e = 0; e < V; ++e) {
-                        const float val = c1 * v1[j][e] + c2 * v2[j][e] + c3 * v3[j][e] + c4 * v4[j][e];
-                        // d(val)/d(w_im) and d(val)/d(h_im)  (cu:86-121)
-                        const float dw = q.hh * (v2[j][e] - v1[j][e]) + q.lh * (v4[j][e] - v3[j][e]);
-                        const float dh = q.hw * (v3[j][e] - v1[j][e]) + q.lw * (v4[j][e] - v2[j][e]);
-                        gw = __fmaf_rn(go[j][e], val, gw);
-                        dxs = __fmaf_rn(go[j][e], dw, dxs);
-                        dys = __fmaf_rn(go[j][e], dh, dys);
-                    }
-                    gxl = __fmaf_rn(dxs, wv[j], gxl);
-                    gyl = __fmaf_rn(dys, wv[j], gyl);
-                    // weight gradient: reduce over the channels of the group
-                    float* gw_dst = p.g_w + (((size_t)ba * NP + pair) * L + l) * d.G;
-                    if (kShfl) {
-                        for (int o = lpg >> 1; o > 0; o >>= 1) gw += __shfl_xor_sync(0xffffffffu, gw, o);
-                        if (act[j] && (lane & (lpg - 1)) == 0) gw_dst[grp[j]] = gw;
-                    } else {
-                        // generic group sizes: stage per-channel terms, then one lane per group sums
-                        float* sc = red + warp * CPAD;
-                        sc[ch[j]] = act[j] ? gw : 0.f;   // V == 1 on this path
-                        __syncwarp();
-                        if (j == NCH - 1) {
-                            for (int g = lane; g < d.G; g += 32) {
-                                float s = 0.f;
-                                for (int c = g * gd; c < (g + 1) * gd; ++c) s += sc[c];
-                                gw_dst[g] = s;
-                            }
-                            __syncwarp();
-                        }
-                    }
-                }
-                gx = __fmaf_rn((float)w, gxl, gx);
-                gy = __fmaf_rn((float)h, gyl, gy);
-            }
+        for (int j = 0; j < NCH; ++j) {
+            VecIO<T, V>::load(q1 + ch[j], r.v[0][j]);
+            VecIO<T, V>::load(q2 + ch[j], r.v[1][j]);
+            VecIO<T, V>::load(q3 + ch[j], r.v[2][j]);
+            VecIO<T, V>::load(q4 + ch[j], r.v[3][j]);
         }
-        if (kMode == kBwd) {
-            gx = warp_sum(gx);
-            gy = warp_sum(gy);
-            if (lane == 0) reinterpret_cast<float2*>(p.g_loc)[(size_t)ba * NP + pair] = make_float2(gx, gy);
+    };
+
+    auto consume = [&](int it, const Item& r) {
+        if (kMode != kBwd) {
+#pragma unroll
+            for (int j = 0; j < NCH; ++j) {
+                float wj = r.wv[j];
+                if (kMode == kFused) wj = expf(wj - sm_m[j]) * sm_inv[j];
+                // weight folded into the four bilinear coefficients: 4 FMAs per channel
+                const float k1 = r.cf.x * wj, k2 = r.cf.y * wj, k3 = r.cf.z * wj, k4 = r.cf.w * wj;
+#pragma unroll
+                for (int e = 0; e < V; ++e) {
+                    float a_ = acc[j][e];
+                    a_ = __fmaf_rn(k1, r.v[0][j][e], a_);
+                    a_ = __fmaf_rn(k2, r.v[1][j][e], a_);
+                    a_ = __fmaf_rn(k3, r.v[2][j][e], a_);
+                    a_ = __fmaf_rn(k4, r.v[3][j][e], a_);
+                    acc[j][e] = a_;
+                }
+            }
+        } else {
+            const float lh = r.cf.x, lw = r.cf.y, hh = 1.f - lh, hw = 1.f - lw;
+            const int ok = __float_as_int(r.cf.z), hwp = __float_as_int(r.cf.w);
+            const bool o1 = ok & 1, o2 = ok & 2, o3 = ok & 4, o4 = ok & 8;
+            // value, d/dw and d/dh as linear forms of the four corner values (cu:86-121)
+            const float c1 = o1 ? hh * hw : 0.f, c2 = o2 ? hh * lw : 0.f, c3 = o3 ? lh * hw : 0.f, c4 = o4 ? lh * lw : 0.f;
+            const float a1 = o1 ? -hh : 0.f, a2 = o2 ? hh : 0.f, a3 = o3 ? -lh : 0.f, a4 = o4 ? lh : 0.f;
+            const float b1 = o1 ? -hw : 0.f, b2 = o2 ? -lw : 0.f, b3 = o3 ? hw : 0.f, b4 = o4 ? lw : 0.f;
+            float gxl = 0.f, gyl = 0.f;
+            float* gw_dst = p.g_w + (((size_t)ba * NP + r.pair) * L + r.l) * d.G;
+#pragma unroll
+            for (int j = 0; j < NCH; ++j) {
+                // s_k = <grad_out, corner_k> over this lane's channels, then three 4-term forms
+                float s1 = 0.f, s2 = 0.f, s3 = 0.f, s4 = 0.f;
+#pragma unroll
+                for (int e = 0; e < V; ++e) {
+                    s1 = __fmaf_rn(go[j][e], r.v[0][j][e], s1);
+                    s2 = __fmaf_rn(go[j][e], r.v[1][j][e], s2);
+                    s3 = __fmaf_rn(go[j][e], r.v[2][j][e], s3);
+                    s4 = __fmaf_rn(go[j][e], r.v[3][j][e], s4);
+                }
+                float gw = c1 * s1 + c2 * s2 + c3 * s3 + c4 * s4;
+                const float dxs = a1 * s1 + a2 * s2 + a3 * s3 + a4 * s4;
+                const float dys = b1 * s1 + b2 * s2 + b3 * s3 + b4 * s4;
+                gxl = __fmaf_rn(dxs, r.wv[j], gxl);
+                gyl = __fmaf_rn(dys, r.wv[j], gyl);
+                // weight gradient: reduce over the channels of the group
+                if (kShfl) {
+                    for (int o = lpg >> 1; o > 0; o >>= 1) gw += __shfl_xor_sync(0xffffffffu, gw, o);
+                    if (act[j] && (lane & (lpg - 1)) == 0) gw_dst[grp[j]] = gw;
+                } else {
+                    // generic group sizes: stage per-channel terms, then one lane per group sums
+                    float* sc = red + warp * CPAD;
+                    sc[j * 32 + lane] = act[j] ? gw : 0.f;   // V == 1 on this path
+                    __syncwarp();
+                    if (j == NCH - 1) {
+                        for (int g = lane; g < d.G; g += 32) {
+                            float s = 0.f;
+                            for (int c = g * gd; c < (g + 1) * gd; ++c) s += sc[c];
+                            gw_dst[g] = s;
+                        }
+                        __syncwarp();
+                    }
+                }
+            }
+            // location gradient of this level; the L levels of a pair are summed in phase 3
+            const float gx = warp_sum((float)(hwp & 0xffff) * gxl);
+            const float gy = warp_sum((float)(hwp >> 16) * gyl);
+            if (lane == 0) s_gxy[it] = make_float2(gx, gy);
+        }
+    };
+
+    if constexpr (NCH * V <= 8) {
+        Item A, B;
+        if (warp < n_items) issue(warp, A);
+        for (int it = warp; it < n_items; it += 2 * kWarps) {
+            const int itB = it + kWarps;
+            if (itB < n_items) issue(itB, B);
+            consume(it, A);
+            const int itA = itB + kWarps;
+            if (itA < n_items) issue(itA, A);
+            if (itB < n_items) consume(itB, B);
+        }
+    } else {   // wide rows: one item's loads already fill the register budget
+        Item A;
+        for (int it = warp; it < n_items; it += kWarps) {
+            issue(it, A);
+            consume(it, A);
+        }
+    }
+
+    if (kMode == kBwd) {
+        // g_loc[pair] = sum over levels, fixed order
+        __syncthreads();
+        for (int i = tid; i < n_list; i += kThreads) {
+            float gx = 0.f, gy = 0.f;
+            for (int l = 0; l < L; ++l) {
+                const float2 g = s_gxy[i * L + l];
+                gx += g.x;
+                gy += g.y;
+            }
+            reinterpret_cast<float2*>(p.g_loc)[(size_t)ba * NP + l_pair[i]] = make_float2(gx, gy);
         }
     }
 

@@ -100,6 +100,21 @@ int hipad_dfa_backward_bf16(const uint16_t *mc_ms_feat,
                             int num_scale, int num_anchors, int num_pts, int num_groups,
                             void *workspace, size_t workspace_bytes, void *stream);
 
+/* Measurement variant of the backward: runs only the kernels selected by stage_mask
+ * (bit0 = sample-major kernel writing grad_weights/grad_sampling_location, bit1 = per-(b,cam,level)
+ * bucket sort into the workspace, bit2 = feature-major reduce writing grad_mc_ms_feat; 7 = the full
+ * backward).  bench.py uses it to put CUDA events around each kernel; results are only meaningful
+ * when the stages are issued in order on one stream with the same workspace. */
+int hipad_dfa_backward_stages(int feat_is_bf16, int stage_mask,
+                              const void *mc_ms_feat,
+                              const int32_t *spatial_shape, const int32_t *scale_start_index,
+                              const float *sample_location, const float *weights,
+                              const float *grad_output,
+                              void *grad_mc_ms_feat, float *grad_sampling_location, float *grad_weights,
+                              int batch_size, int num_cams, int num_feat, int num_embeds,
+                              int num_scale, int num_anchors, int num_pts, int num_groups,
+                              void *workspace, size_t workspace_bytes, void *stream);
+
 /* ---- integer sampling contract (parity instrument) ----
  * indices: int32 [bs, A, P, cams, L, 6] = {valid, h_low, w_low, level_offset, corner_mask, row0},
  * computed by the SAME device routine the kernels above use
