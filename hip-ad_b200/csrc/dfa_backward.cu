@@ -43,6 +43,7 @@ int launch_reduce(const GfeatParams& gp, KernelShape ks, dim3 grid, cudaStream_t
     if (ks.vector) {
         if (ks.nch == 1) HIPAD_RED(VV, 1);
         if (ks.nch == 2) HIPAD_RED(VV, 2);
+        if (ks.nch == 3) HIPAD_RED(VV, 3);
         if (ks.nch == 4) HIPAD_RED(VV, 4);
     } else {
         if (ks.nch == 2) HIPAD_RED(1, 2);
@@ -62,7 +63,7 @@ int launch_backward(const BwdArgs& a) {
                     (reinterpret_cast<uintptr_t>(a.grad_out) % 16 == 0) &&
                     (reinterpret_cast<uintptr_t>(a.g_w) % 16 == 0);
     const KernelShape ks = pick_shape(a.type, d.C, d.G, al);
-    if (!ks.ok || d.cams * d.L > kMaxCamLevels || (long long)d.num_feat * d.C >= (1LL << 31)) return -2;
+    if (!ks.ok || d.cams * d.L > kMaxCamLevels || (long long)d.num_feat * d.C >= (1LL << 30)) return -2;
     const WorkspaceLayout wl = workspace_layout(d);
     if (a.workspace == nullptr || a.workspace_bytes < wl.total ||
         reinterpret_cast<uintptr_t>(a.workspace) % kAlign != 0)

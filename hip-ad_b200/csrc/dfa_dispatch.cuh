@@ -15,9 +15,9 @@ inline cudaError_t ensure_smem(K kern, size_t smem) {
     return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 }
 
-template <typename T, int V, int NCH, int kL, int kMode, bool kShfl, bool kCluster>
+template <typename T, int V, int NCH, int kL, int kMode, int kLPG, bool kCluster>
 int launch_sample_inst(const SampleParams& p, int grid, size_t smem, cudaStream_t st) {
-    auto kern = dfa_sample_kernel<T, V, NCH, kL, kMode, kShfl, kCluster, kSampleWarps>;
+    auto kern = dfa_sample_kernel<T, V, NCH, kL, kMode, kLPG, kCluster, kSampleWarps>;
     cudaError_t e = ensure_smem(kern, smem);
     if (e != cudaSuccess) return (int)e;
     cudaLaunchConfig_t cfg = {};
@@ -42,15 +42,19 @@ template <typename T, int kMode, bool kCluster>
 int dispatch_sample(const SampleParams& p, KernelShape ks, int grid, size_t smem, cudaStream_t st) {
     constexpr int VV = 16 / (int)sizeof(T);
     const bool l4 = (p.d.L == 4);
-#define HIPAD_CASE(V_, NCH_, KL_, SHFL_) \
-    return launch_sample_inst<T, V_, NCH_, KL_, kMode, SHFL_, kCluster>(p, grid, smem, st)
+    const int lpg = (p.d.C / p.d.G) / VV;
+#define HIPAD_CASE(V_, NCH_, KL_, LPG_) \
+    return launch_sample_inst<T, V_, NCH_, KL_, kMode, LPG_, kCluster>(p, grid, smem, st)
     if (ks.vector) {
-        if (ks.nch == 1) { if (l4) HIPAD_CASE(VV, 1, 4, true); else HIPAD_CASE(VV, 1, 0, true); }
-        if (ks.nch == 2) { if (l4) HIPAD_CASE(VV, 2, 4, true); else HIPAD_CASE(VV, 2, 0, true); }
-        if (ks.nch == 4) { if (l4) HIPAD_CASE(VV, 4, 4, true); else HIPAD_CASE(VV, 4, 0, true); }
+        // the shipped HiP-AD shape (C=256, G=8, L=4) gets fully compile-time reductions
+        if (kMode == kBwd && l4 && ks.nch == 32 / VV * 8 / 32 && lpg == 32 / VV) HIPAD_CASE(VV, 32 / VV * 8 / 32, 4, 32 / VV);
+        if (ks.nch == 1) { if (l4) HIPAD_CASE(VV, 1, 4, 0); else HIPAD_CASE(VV, 1, 0, 0); }
+        if (ks.nch == 2) { if (l4) HIPAD_CASE(VV, 2, 4, 0); else HIPAD_CASE(VV, 2, 0, 0); }
+        if (ks.nch == 3) { if (l4) HIPAD_CASE(VV, 3, 4, 0); else HIPAD_CASE(VV, 3, 0, 0); }
+        if (ks.nch == 4) { if (l4) HIPAD_CASE(VV, 4, 4, 0); else HIPAD_CASE(VV, 4, 0, 0); }
     } else {
-        if (ks.nch == 2) HIPAD_CASE(1, 2, 0, false);
-        if (ks.nch == 8) HIPAD_CASE(1, 8, 0, false);
+        if (ks.nch == 2) HIPAD_CASE(1, 2, 0, -1);
+        if (ks.nch == 8) HIPAD_CASE(1, 8, 0, -1);
     }
 #undef HIPAD_CASE
     return -2;

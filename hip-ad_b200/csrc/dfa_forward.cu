@@ -8,10 +8,10 @@ KernelShape pick_shape(ElemType t, int C, int G, bool aligned16) {
     const int V = (t == kF32) ? 4 : 8;
     const int gd = C / G;
     const bool pow2_lanes = (gd % V == 0) && (((gd / V) & ((gd / V) - 1)) == 0) && (gd / V) <= 32;
-    if (aligned16 && C % V == 0 && pow2_lanes && C <= 4 * 32 * V) {
+    // vector path: a single (possibly partial) 32-lane chunk, or 2..4 FULL chunks
+    if (aligned16 && C % V == 0 && pow2_lanes && (C <= 32 * V || (C % (32 * V) == 0 && C <= 4 * 32 * V))) {
         ks.vector = true;
-        const int chunks = (C + 32 * V - 1) / (32 * V);
-        ks.nch = chunks <= 1 ? 1 : (chunks <= 2 ? 2 : 4);
+        ks.nch = (C + 32 * V - 1) / (32 * V);
         ks.ok = true;
         return ks;
     }
@@ -35,7 +35,7 @@ int launch_forward(const FwdArgs& a) {
     const bool al = (reinterpret_cast<uintptr_t>(a.feat) % 16 == 0) &&
                     (reinterpret_cast<uintptr_t>(a.out) % 16 == 0);
     const KernelShape ks = pick_shape(a.type, d.C, d.G, al);
-    if (!ks.ok || d.cams * d.L > kMaxCamLevels || (long long)d.num_feat * d.C >= (1LL << 31)) return -2;
+    if (!ks.ok || d.cams * d.L > kMaxCamLevels || (long long)d.num_feat * d.C >= (1LL << 30)) return -2;
     const int mode = a.fused ? kFused : kFwd;
     if (a.fused && ((kSampleWarps * 32) % d.G != 0)) return -2;
 

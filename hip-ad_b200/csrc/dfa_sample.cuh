@@ -71,7 +71,7 @@ __device__ __forceinline__ int block_compact_offset(bool flag, int* s_wcnt, int&
 // shared-memory carve-up, as byte OFFSETS from the dynamic-smem base (all multiples of 16) so the
 // compiler keeps every access in the shared address space (LDS/STS, 32-bit addressing).
 struct SampleSmem {
-    int tab, wcnt, red, part, lxy, lpair, mrows, mcoef, valid, gxy, proj, stat, red2, total;
+    int tab, wcnt, red, part, lxy, lpair, mrows, mcoef, mwoff, valid, mdx, mdy, proj, stat, red2, total;
 };
 template <int kWarps>
 __host__ __device__ inline SampleSmem sample_smem_layout(int mode, int n_cl, int L, int cpad, int ps, int G, int cams) {
@@ -86,8 +86,10 @@ __host__ __device__ inline SampleSmem sample_smem_layout(int mode, int n_cl, int
     o.lpair = take(ps * 4);                //                 pair ids
     o.mrows = take(ps * L * 16);           // per (visible pair, level): 4 corner rows
     o.mcoef = take(ps * L * 16);           //                            4 bilinear terms
+    o.mwoff = take(ps * L * 4);            //                            weight offset
     o.valid = take(mode == kBwd ? ps : 0);
-    o.gxy = take(mode == kBwd ? ps * L * 8 : 0);   // per (pair, level) location-gradient partials
+    o.mdx = take(mode == kBwd ? ps * L * 16 : 0);  // bwd: d/dx coefficient vectors (scaled by W)
+    o.mdy = take(mode == kBwd ? ps * L * 16 : 0);  //      d/dy coefficient vectors (scaled by H)
     o.proj = take(mode == kFused ? cams * 14 * 4 : 0);
     o.stat = take(mode == kFused ? 4 * G * 4 : 0);
     o.red2 = take(mode == kFused ? 2 * kWarps * 32 * 4 : 0);
@@ -95,7 +97,8 @@ __host__ __device__ inline SampleSmem sample_smem_layout(int mode, int n_cl, int
     return o;
 }
 
-template <typename T, int V, int NCH, int kL, int kMode, bool kShfl, bool kCluster, int kWarps>
+// kLPG: lanes per channel group. >0 compile-time (power of two), 0 run-time (power of two), -1 generic groups
+template <typename T, int V, int NCH, int kL, int kMode, int kLPG, bool kCluster, int kWarps>
 __global__ void __launch_bounds__(kWarps * 32) dfa_sample_kernel(const SampleParams p) {
     constexpr int kThreads = kWarps * 32;
     constexpr int CPAD = NCH * 32 * V;
@@ -121,9 +124,11 @@ __global__ void __launch_bounds__(kWarps * 32) dfa_sample_kernel(const SamplePar
     float2* l_xy = reinterpret_cast<float2*>(smem_raw + so.lxy);
     int* l_pair = reinterpret_cast<int*>(smem_raw + so.lpair);
     int4* m_rows = reinterpret_cast<int4*>(smem_raw + so.mrows);     // element rows of the 4 corners (clamped)
-    float4* m_coef = reinterpret_cast<float4*>(smem_raw + so.mcoef); // fwd: c1..c4   bwd: lh, lw, ok, (h<<16|w)
+    float4* m_coef = reinterpret_cast<float4*>(smem_raw + so.mcoef); // c1..c4 (0 for out-of-bounds corners)
+    int* m_woff = reinterpret_cast<int*>(smem_raw + so.mwoff);
     unsigned char* s_valid = smem_raw + so.valid;
-    float2* s_gxy = reinterpret_cast<float2*>(smem_raw + so.gxy);
+    float4* m_dx = reinterpret_cast<float4*>(smem_raw + so.mdx);
+    float4* m_dy = reinterpret_cast<float4*>(smem_raw + so.mdy);
     float* s_proj = reinterpret_cast<float*>(smem_raw + so.proj);    // kFused: cams*12 matrix rows 0..2, cams*2 wh
     float* s_stat = reinterpret_cast<float*>(smem_raw + so.stat);    // kFused: m[G], inv_s[G], scratch 2*G
     float* s_red2 = reinterpret_cast<float*>(smem_raw + so.red2);    // kFused: per-thread (m,s)
@@ -274,19 +279,28 @@ __global__ void __launch_bounds__(kWarps * 32) dfa_sample_kernel(const SamplePar
         const int i = it / L, l = it - i * L;
         const float2 xy = l_xy[i];
         const int pair = l_pair[i];
-        const int cam = pair - (pair / d.cams) * d.cams;
+        const int pt = pair / d.cams, cam = pair - pt * d.cams;
         const int* t = tab + (cam * L + l) * 3;
         const int h = t[0], w = t[1];
         const Quad q = quad_setup(xy.x, xy.y, h, w);
         const int r1 = t[2] + q.h_low * w + q.w_low, r2 = r1 + 1, r3 = r1 + w, r4 = r3 + 1;
         const int safe = q.ok1 ? r1 : (q.ok2 ? r2 : (q.ok3 ? r3 : r4));
-        m_rows[it] = make_int4(q.ok1 ? r1 : safe, q.ok2 ? r2 : safe, q.ok3 ? r3 : safe, q.ok4 ? r4 : safe);
-        if (kMode != kBwd) {
-            m_coef[it] = make_float4(q.ok1 ? q.hh * q.hw : 0.f, q.ok2 ? q.hh * q.lw : 0.f,
-                                     q.ok3 ? q.lh * q.hw : 0.f, q.ok4 ? q.lh * q.lw : 0.f);
-        } else {
-            const int ok = (int)q.ok1 | ((int)q.ok2 << 1) | ((int)q.ok3 << 2) | ((int)q.ok4 << 3);
-            m_coef[it] = make_float4(q.lh, q.lw, __int_as_float(ok), __int_as_float((h << 16) | w));
+        // BYTE offsets of the corner rows inside this batch element (< 2^32, checked on the host)
+        const unsigned row_bytes = (unsigned)d.C * (unsigned)sizeof(T);
+        m_rows[it] = make_int4((int)((unsigned)(q.ok1 ? r1 : safe) * row_bytes), (int)((unsigned)(q.ok2 ? r2 : safe) * row_bytes),
+                               (int)((unsigned)(q.ok3 ? r3 : safe) * row_bytes), (int)((unsigned)(q.ok4 ? r4 : safe) * row_bytes));
+        // element offset of this item's G weights inside the output row's weight block
+        m_woff[it] = (kMode == kFused) ? ((cam * L + l) * d.P + pt) * d.G : (pair * L + l) * d.G;
+        m_coef[it] = make_float4(q.ok1 ? q.hh * q.hw : 0.f, q.ok2 ? q.hh * q.lw : 0.f,
+                                 q.ok3 ? q.lh * q.hw : 0.f, q.ok4 ? q.lh * q.lw : 0.f);
+        if (kMode == kBwd) {
+            // d(val)/d(loc_x) = W * (-hh v1 + hh v2 - lh v3 + lh v4), d/d(loc_y) = H * (-hw v1 - lw v2 + hw v3 + lw v4)
+            // (cu:86-125), as coefficient vectors with out-of-bounds corners zeroed
+            const float W_ = (float)w, H_ = (float)h;
+            m_dx[it] = make_float4(q.ok1 ? -q.hh * W_ : 0.f, q.ok2 ? q.hh * W_ : 0.f,
+                                   q.ok3 ? -q.lh * W_ : 0.f, q.ok4 ? q.lh * W_ : 0.f);
+            m_dy[it] = make_float4(q.ok1 ? -q.hw * H_ : 0.f, q.ok2 ? -q.lw * H_ : 0.f,
+                                   q.ok3 ? q.hw * H_ : 0.f, q.ok4 ? q.lw * H_ : 0.f);
         }
     }
     __syncthreads();
@@ -311,7 +325,7 @@ __global__ void __launch_bounds__(kWarps * 32) dfa_sample_kernel(const SamplePar
             sm_inv[j] = s_stat[d.G + grp[j]];
         }
     }
-    const int lpg = (gd / V) > 0 ? (gd / V) : 1;   // lanes per group (kShfl: power of two <= 32)
+    const int lpg = (kLPG > 0) ? kLPG : ((gd / V) > 0 ? (gd / V) : 1);   // lanes per group (power of two <= 32 unless kLPG < 0)
 
     float acc[NCH][V];
     float go[NCH][V];
@@ -325,144 +339,192 @@ __global__ void __launch_bounds__(kWarps * 32) dfa_sample_kernel(const SamplePar
             if (act[j]) VecIO<float, V>::load(p.grad_out + (size_t)ba * d.C + ch[j], go[j]);   // inactive: stays 0
     }
 
-    // element offsets inside one batch element fit 32 bits (num_feat*C < 2^31, checked on the host)
-    const T* featb = reinterpret_cast<const T*>(p.feat) + (size_t)b * d.num_feat * d.C;
-    const unsigned Cu = (unsigned)d.C;
+    // Addressing: one 64-bit base per tensor (uniform), everything else 32-bit.  On the vector path
+    // with NCH > 1 every lane is active (C == NCH*32*V), so chunk j is a compile-time constant
+    // offset from chunk 0 and folds into the load's immediate field.
+    const char* featb = reinterpret_cast<const char*>(p.feat) + (size_t)b * d.num_feat * d.C * sizeof(T);
+    const unsigned lane_byte = (unsigned)ch[0] * (unsigned)sizeof(T);
+    const float* wblock = (kMode == kFused) ? p.weights + (size_t)ba * d.cams * L * d.P * d.G
+                                            : p.weights + (size_t)ba * NP * L * d.G;
     const int n_items = n_list * L;
+    constexpr bool kConstChunks = (V > 1);   // vector path: full chunks (host guarantees it when NCH > 1)
 
     struct Item {
         float v[4][NCH][V];
         float wv[NCH];
         float4 cf;
-        int pair, l;
+        int woff;
     };
 
+    // Warp `warp` owns visible pairs warp, warp+kWarps, ... and walks their L levels back to back
+    // (sequence index q -> pair warp + kWarps*(q / L), level q % L), so location gradients
+    // accumulate in-lane over the levels and need one warp reduction per PAIR.
+    const int my_pairs = (n_list > warp) ? (n_list - warp + kWarps - 1) / kWarps : 0;
+    const int my_items = my_pairs * L;
+    auto item_of = [&](int q) { const int k = q / L; return (warp + k * kWarps) * L + (q - k * L); };
+
     auto issue = [&](int it, Item& r) {
-        const int i = it / L;
-        r.l = it - i * L;
-        r.pair = l_pair[i];
         const int4 rw = m_rows[it];
         r.cf = m_coef[it];
-        const int pt = r.pair / d.cams, cam = r.pair - pt * d.cams;
-        const float* wrow = (kMode == kFused)
-                                ? p.weights + (((size_t)ba * d.cams + cam) * L + r.l) * d.P * d.G + (size_t)pt * d.G
-                                : p.weights + (((size_t)ba * NP + r.pair) * L + r.l) * d.G;
-#pragma unroll
-        for (int j = 0; j < NCH; ++j) r.wv[j] = __ldg(wrow + grp[j]);
-        // one 64-bit row pointer per corner; the NCH chunks are constant offsets from it
-        const T* q1 = featb + (size_t)((unsigned)rw.x * Cu);
-        const T* q2 = featb + (size_t)((unsigned)rw.y * Cu);
-        const T* q3 = featb + (size_t)((unsigned)rw.z * Cu);
-        const T* q4 = featb + (size_t)((unsigned)rw.w * Cu);
+        r.woff = m_woff[it];
+        const float* wp = wblock + (unsigned)(r.woff + grp[0]);
+        const char* q1 = featb + ((unsigned)rw.x + lane_byte);
+        const char* q2 = featb + ((unsigned)rw.y + lane_byte);
+        const char* q3 = featb + ((unsigned)rw.z + lane_byte);
+        const char* q4 = featb + ((unsigned)rw.w + lane_byte);
 #pragma unroll
         for (int j = 0; j < NCH; ++j) {
-            VecIO<T, V>::load(q1 + ch[j], r.v[0][j]);
-            VecIO<T, V>::load(q2 + ch[j], r.v[1][j]);
-            VecIO<T, V>::load(q3 + ch[j], r.v[2][j]);
-            VecIO<T, V>::load(q4 + ch[j], r.v[3][j]);
+            const int dj = kConstChunks ? j * 32 * V : ch[j] - ch[0];          // channels
+            r.wv[j] = __ldg(wp + (grp[j] - grp[0]));
+            VecIO<T, V>::load(reinterpret_cast<const T*>(q1) + dj, r.v[0][j]);
+            VecIO<T, V>::load(reinterpret_cast<const T*>(q2) + dj, r.v[1][j]);
+            VecIO<T, V>::load(reinterpret_cast<const T*>(q3) + dj, r.v[2][j]);
+            VecIO<T, V>::load(reinterpret_cast<const T*>(q4) + dj, r.v[3][j]);
         }
     };
 
-    auto consume = [&](int it, const Item& r) {
+    float gx = 0.f, gy = 0.f;   // kBwd: lane partials of the current pair's location gradient
+    float* const gw_block = (kMode == kBwd) ? p.g_w + (size_t)ba * NP * L * d.G : nullptr;
+    float* const gloc_row = (kMode == kBwd) ? p.g_loc + (size_t)ba * NP * 2 : nullptr;
+
+    auto consume = [&](int q, int it, const Item& r) {
         if (kMode != kBwd) {
 #pragma unroll
             for (int j = 0; j < NCH; ++j) {
                 float wj = r.wv[j];
                 if (kMode == kFused) wj = expf(wj - sm_m[j]) * sm_inv[j];
-                // weight folded into the four bilinear coefficients: 4 FMAs per channel
-                const float k1 = r.cf.x * wj, k2 = r.cf.y * wj, k3 = r.cf.z * wj, k4 = r.cf.w * wj;
+                // weight folded into the four bilinear coefficients: 4 FMAs per channel,
+                // issued as packed fp32x2 FMAs (FFMA2) where the vector width allows
+                const float kk[4] = {r.cf.x * wj, r.cf.y * wj, r.cf.z * wj, r.cf.w * wj};
+                if constexpr (V % 2 == 0) {
 #pragma unroll
-                for (int e = 0; e < V; ++e) {
-                    float a_ = acc[j][e];
-                    a_ = __fmaf_rn(k1, r.v[0][j][e], a_);
-                    a_ = __fmaf_rn(k2, r.v[1][j][e], a_);
-                    a_ = __fmaf_rn(k3, r.v[2][j][e], a_);
-                    a_ = __fmaf_rn(k4, r.v[3][j][e], a_);
-                    acc[j][e] = a_;
+                    for (int e = 0; e < V; e += 2) {
+                        float2 a2 = make_float2(acc[j][e], acc[j][e + 1]);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            a2 = __ffma2_rn(make_float2(kk[k], kk[k]), make_float2(r.v[k][j][e], r.v[k][j][e + 1]), a2);
+                        acc[j][e] = a2.x;
+                        acc[j][e + 1] = a2.y;
+                    }
+                } else {
+#pragma unroll
+                    for (int e = 0; e < V; ++e)
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) acc[j][e] = __fmaf_rn(kk[k], r.v[k][j][e], acc[j][e]);
                 }
             }
         } else {
-            const float lh = r.cf.x, lw = r.cf.y, hh = 1.f - lh, hw = 1.f - lw;
-            const int ok = __float_as_int(r.cf.z), hwp = __float_as_int(r.cf.w);
-            const bool o1 = ok & 1, o2 = ok & 2, o3 = ok & 4, o4 = ok & 8;
-            // value, d/dw and d/dh as linear forms of the four corner values (cu:86-121)
-            const float c1 = o1 ? hh * hw : 0.f, c2 = o2 ? hh * lw : 0.f, c3 = o3 ? lh * hw : 0.f, c4 = o4 ? lh * lw : 0.f;
-            const float a1 = o1 ? -hh : 0.f, a2 = o2 ? hh : 0.f, a3 = o3 ? -lh : 0.f, a4 = o4 ? lh : 0.f;
-            const float b1 = o1 ? -hw : 0.f, b2 = o2 ? -lw : 0.f, b3 = o3 ? hw : 0.f, b4 = o4 ? lw : 0.f;
-            float gxl = 0.f, gyl = 0.f;
-            float* gw_dst = p.g_w + (((size_t)ba * NP + r.pair) * L + r.l) * d.G;
+            const float4 cx4 = m_dx[it], cy4 = m_dy[it];
+            const float cc[4] = {r.cf.x, r.cf.y, r.cf.z, r.cf.w};
+            const float ax[4] = {cx4.x, cx4.y, cx4.z, cx4.w};
+            const float by[4] = {cy4.x, cy4.y, cy4.z, cy4.w};
+            float* gw_dst = gw_block + (unsigned)r.woff;
+            float gwv[NCH];
 #pragma unroll
             for (int j = 0; j < NCH; ++j) {
                 // s_k = <grad_out, corner_k> over this lane's channels, then three 4-term forms
-                float s1 = 0.f, s2 = 0.f, s3 = 0.f, s4 = 0.f;
+                float sk[4];
 #pragma unroll
-                for (int e = 0; e < V; ++e) {
-                    s1 = __fmaf_rn(go[j][e], r.v[0][j][e], s1);
-                    s2 = __fmaf_rn(go[j][e], r.v[1][j][e], s2);
-                    s3 = __fmaf_rn(go[j][e], r.v[2][j][e], s3);
-                    s4 = __fmaf_rn(go[j][e], r.v[3][j][e], s4);
-                }
-                float gw = c1 * s1 + c2 * s2 + c3 * s3 + c4 * s4;
-                const float dxs = a1 * s1 + a2 * s2 + a3 * s3 + a4 * s4;
-                const float dys = b1 * s1 + b2 * s2 + b3 * s3 + b4 * s4;
-                gxl = __fmaf_rn(dxs, r.wv[j], gxl);
-                gyl = __fmaf_rn(dys, r.wv[j], gyl);
-                // weight gradient: reduce over the channels of the group
-                if (kShfl) {
-                    for (int o = lpg >> 1; o > 0; o >>= 1) gw += __shfl_xor_sync(0xffffffffu, gw, o);
-                    if (act[j] && (lane & (lpg - 1)) == 0) gw_dst[grp[j]] = gw;
-                } else {
-                    // generic group sizes: stage per-channel terms, then one lane per group sums
-                    float* sc = red + warp * CPAD;
-                    sc[j * 32 + lane] = act[j] ? gw : 0.f;   // V == 1 on this path
-                    __syncwarp();
-                    if (j == NCH - 1) {
-                        for (int g = lane; g < d.G; g += 32) {
-                            float s = 0.f;
-                            for (int c = g * gd; c < (g + 1) * gd; ++c) s += sc[c];
-                            gw_dst[g] = s;
-                        }
-                        __syncwarp();
+                for (int k = 0; k < 4; ++k) {
+                    if constexpr (V % 2 == 0) {
+                        float2 s2 = make_float2(0.f, 0.f);
+#pragma unroll
+                        for (int e = 0; e < V; e += 2)
+                            s2 = __ffma2_rn(make_float2(go[j][e], go[j][e + 1]),
+                                            make_float2(r.v[k][j][e], r.v[k][j][e + 1]), s2);
+                        sk[k] = s2.x + s2.y;
+                    } else {
+                        float s1 = 0.f;
+#pragma unroll
+                        for (int e = 0; e < V; ++e) s1 = __fmaf_rn(go[j][e], r.v[k][j][e], s1);
+                        sk[k] = s1;
                     }
                 }
+                gwv[j] = cc[0] * sk[0] + cc[1] * sk[1] + cc[2] * sk[2] + cc[3] * sk[3];
+                const float dxs = ax[0] * sk[0] + ax[1] * sk[1] + ax[2] * sk[2] + ax[3] * sk[3];
+                const float dys = by[0] * sk[0] + by[1] * sk[1] + by[2] * sk[2] + by[3] * sk[3];
+                gx = __fmaf_rn(dxs, r.wv[j], gx);
+                gy = __fmaf_rn(dys, r.wv[j], gy);
             }
-            // location gradient of this level; the L levels of a pair are summed in phase 3
-            const float gx = warp_sum((float)(hwp & 0xffff) * gxl);
-            const float gy = warp_sum((float)(hwp >> 16) * gyl);
-            if (lane == 0) s_gxy[it] = make_float2(gx, gy);
+            // weight gradient: reduce over the lanes of each channel group, then one store per group
+            if (kLPG >= 0) {
+                if constexpr (NCH == 2) {
+                    // two group sums per lane: the first butterfly step also splits them between the
+                    // halves of the lane group (3 shuffles instead of 6 for 8-lane groups)
+                    if (lpg >= 2) {
+                        const int half = lpg >> 1;
+                        const bool up = (lane & half) != 0;
+                        const float send = up ? gwv[0] : gwv[1];
+                        float keep = up ? gwv[1] : gwv[0];
+                        keep += __shfl_xor_sync(0xffffffffu, send, half);
+#pragma unroll
+                        for (int o = 8; o > 0; o >>= 1)
+                            if (o < half) keep += __shfl_xor_sync(0xffffffffu, keep, o);
+                        const int sub = lane & (lpg - 1);
+                        if (sub == 0) gw_dst[grp[0]] = keep;
+                        if (sub == half) gw_dst[grp[1]] = keep;
+                    } else {
+                        gw_dst[grp[0]] = gwv[0];
+                        gw_dst[grp[1]] = gwv[1];
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < NCH; ++j) {
+                        float gw = gwv[j];
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1)
+                            if (o < lpg) gw += __shfl_xor_sync(0xffffffffu, gw, o);
+                        if (act[j] && (lane & (lpg - 1)) == 0) gw_dst[grp[j]] = gw;
+                    }
+                }
+            } else {
+                // generic group sizes (V == 1): stage per-channel terms, one lane per group sums
+                float* sc = red + warp * CPAD;
+#pragma unroll
+                for (int j = 0; j < NCH; ++j) sc[j * 32 + lane] = act[j] ? gwv[j] : 0.f;
+                __syncwarp();
+                for (int g = lane; g < d.G; g += 32) {
+                    float s_ = 0.f;
+                    for (int c = g * gd; c < (g + 1) * gd; ++c) s_ += sc[c];
+                    gw_dst[g] = s_;
+                }
+                __syncwarp();
+            }
+            if (q % L == L - 1) {
+                // last level of the pair: gx and gy reduced together (lower half-warp ends with gx,
+                // upper with gy: 5 shuffles instead of 10)
+                const bool up = (lane & 16) != 0;
+                const float send = up ? gx : gy;
+                float keep = up ? gy : gx;
+                keep += __shfl_xor_sync(0xffffffffu, send, 16);
+#pragma unroll
+                for (int o = 8; o > 0; o >>= 1) keep += __shfl_xor_sync(0xffffffffu, keep, o);
+                const int pair = l_pair[it / L];
+                if ((lane & 15) == 0) gloc_row[pair * 2 + (up ? 1 : 0)] = keep;
+                gx = 0.f;
+                gy = 0.f;
+            }
         }
     };
 
     if constexpr (NCH * V <= 8) {
         Item A, B;
-        if (warp < n_items) issue(warp, A);
-        for (int it = warp; it < n_items; it += 2 * kWarps) {
-            const int itB = it + kWarps;
-            if (itB < n_items) issue(itB, B);
-            consume(it, A);
-            const int itA = itB + kWarps;
-            if (itA < n_items) issue(itA, A);
-            if (itB < n_items) consume(itB, B);
+        if (my_items > 0) issue(item_of(0), A);
+        for (int q = 0; q < my_items; q += 2) {
+            const int itA = item_of(q);
+            const bool hasB = q + 1 < my_items;
+            const int itB = hasB ? item_of(q + 1) : 0;
+            if (hasB) issue(itB, B);
+            consume(q, itA, A);
+            if (q + 2 < my_items) issue(item_of(q + 2), A);
+            if (hasB) consume(q + 1, itB, B);
         }
     } else {   // wide rows: one item's loads already fill the register budget
         Item A;
-        for (int it = warp; it < n_items; it += kWarps) {
+        for (int q = 0; q < my_items; ++q) {
+            const int it = item_of(q);
             issue(it, A);
-            consume(it, A);
-        }
-    }
-
-    if (kMode == kBwd) {
-        // g_loc[pair] = sum over levels, fixed order
-        __syncthreads();
-        for (int i = tid; i < n_list; i += kThreads) {
-            float gx = 0.f, gy = 0.f;
-            for (int l = 0; l < L; ++l) {
-                const float2 g = s_gxy[i * L + l];
-                gx += g.x;
-                gy += g.y;
-            }
-            reinterpret_cast<float2*>(p.g_loc)[(size_t)ba * NP + l_pair[i]] = make_float2(gx, gy);
+            consume(q, it, A);
         }
     }
 
