@@ -88,6 +88,27 @@ def algorithmic_bytes(ops, shapes_d, starts_d, loc_d, bs, F, A, P, L, elem_bytes
                 bwd_sample=b_bwd - bs * F * C * elem_bytes)
 
 
+# ------------------------------------------------------------------------------------- multi-GPU
+def shard_seed(rank):
+    """Batch sharding: rank r owns its own `bs` samples (seeded by rank); the ranks share nothing and
+    the data path has no collective.  Only the timing is reduced (MAX) across ranks."""
+    return rank
+
+
+def max_over_ranks(value, device):
+    """MAX-reduce a python float across the process group (identity when not initialised)."""
+    import torch.distributed as dist
+    t = torch.tensor([value], device=device, dtype=torch.float64)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def whole_job_gbs(world, bytes_per_rank_step, ms_per_step):
+    """Aggregate throughput of the job: every rank moves `bytes_per_rank_step` per step (weak scaling)."""
+    return world * bytes_per_rank_step / (ms_per_step * 1e-3) / 1e9
+
+
 # ------------------------------------------------------------------------------------- clocks
 class ClockSampler:
     QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
@@ -160,8 +181,8 @@ def gpu_arm(args):
     bs = args.bs
     L = 4
 
-    calls, shapes, starts, F = make_calls(bs, seed=rank)
-    rng = np.random.default_rng(1234 + rank)
+    calls, shapes, starts, F = make_calls(bs, seed=shard_seed(rank))
+    rng = np.random.default_rng(1234 + shard_seed(rank))
     feat_h = torch.from_numpy(rng.standard_normal((bs, F, C), dtype=np.float32))
     if bf16:
         feat_h = feat_h.bfloat16()
@@ -255,13 +276,9 @@ def gpu_arm(args):
         barrier()
         step_ms = [a.elapsed_time(b) for a, b in ev]
         clocks = sampler.stop() if rank == 0 else None
-    total_ms = float(sum(step_ms))
-    t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms = float(t.item())
+    total_ms = max_over_ranks(float(sum(step_ms)), dev)
     ms_per_step = total_ms / args.steps
-    value = world * step_bytes / (ms_per_step * 1e-3) / 1e9
+    value = whole_job_gbs(world, step_bytes, ms_per_step)
 
     # ---- per-kernel timing (CUDA events on the launching stream), for the roofline object
     kern = {"dfa_sample_kernel<fwd>": [], "dfa_sample_kernel<bwd>": [], "dfa_bucket_sort_kernel": [],
@@ -383,12 +400,10 @@ def gpu_arm(args):
         for _ in range(n_e2e):
             e2e_step()
         torch.cuda.synchronize()
-        dt = torch.tensor([(time.perf_counter() - t0) / n_e2e], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-        e2e = {"value": round(world * step_bytes / float(dt.item()) / 1e9, 2), "unit": "GB/s",
+        dt_s = max_over_ranks((time.perf_counter() - t0) / n_e2e, dev)
+        e2e = {"value": round(whole_job_gbs(world, step_bytes, dt_s * 1e3), 2), "unit": "GB/s",
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-               "ms_per_step": round(float(dt.item()) * 1e3, 3), "steps": n_e2e,
+               "ms_per_step": round(dt_s * 1e3, 3), "steps": n_e2e,
                "api": "hipad_b200.deformable_aggregation_function + autograd, pinned host buffers"}
 
     cpu_baseline = None

@@ -48,7 +48,7 @@ def build(force=False, verbose=False):
 
     with concurrent.futures.ThreadPoolExecutor(len(SOURCES)) as ex:
         objs = list(ex.map(compile_one, SOURCES))
-    cmd = ["nvcc", "-shared", "-o", LIB_PATH] + objs + ["-lcudart"]
+    cmd = ["nvcc", "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB_PATH] + objs + ["-lcudart"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed: %s\n%s" % (" ".join(cmd), r.stdout + r.stderr))
