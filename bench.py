@@ -224,7 +224,9 @@ def gpu_arm(args):
         for c in reversed(calls):       # autograd order
             bwd_call(c, stream)
 
-    launches_per_step = len(calls) * (1 + 4)
+    # per call: forward sample kernel; backward = sample kernel (+ its own zero-fill kernel when the grid is too
+    # small to fold the fill in: the ego call), visible compaction, band sort, touched-row reduce, heavy-row reduce
+    launches_per_step = sum(1 + 5 + (1 if bs * c["A"] * 8 < 2 * 148 else 0) for c in calls)
     flush = torch.zeros(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
     def flush_l2():
@@ -281,8 +283,8 @@ def gpu_arm(args):
     value = whole_job_gbs(world, step_bytes, ms_per_step)
 
     # ---- per-kernel timing (CUDA events on the launching stream), for the roofline object
-    kern = {"dfa_sample_kernel<fwd>": [], "dfa_sample_kernel<bwd>": [], "dfa_bucket_sort_kernel": [],
-            "dfa_gfeat_reduce_kernel": []}
+    kern = {"dfa_sample_kernel<fwd>": [], "dfa_sample_kernel<bwd>+zero_fill": [], "dfa_vis_compact+band_sort": [],
+            "dfa_gfeat_rows+heavy": []}
     kbytes = {k: [] for k in kern}
     per_mod = {}
     with torch.cuda.stream(stream):
@@ -302,8 +304,9 @@ def gpu_arm(args):
             for c in calls:
                 e = c["_ev"]
                 d = [e[i].elapsed_time(e[i + 1]) * 1e3 for i in range(4)]   # microseconds
-                for name, dur, nb in zip(kern, d, (c["bytes"]["fwd"], c["bytes"]["bwd_sample"], 0,
-                                                   c["bytes"]["dense_gfeat"])):
+                # algorithmic bytes per stage: forward B_fwd; backward sample kernel B_bwd (it also performs the
+                # dense g_feat write); the sort and the touched-row reduce move no algorithmic bytes of their own
+                for name, dur, nb in zip(kern, d, (c["bytes"]["fwd"], c["bytes"]["bwd"], 0, 0)):
                     kern[name].append(dur)
                     kbytes[name].append(nb)
                 m = per_mod.setdefault(c["kind"], dict(fwd_us=[], bwd_us=[], bytes=c["bytes"]))

@@ -54,7 +54,8 @@ int backward_common(ElemType t, const void* feat, const int32_t* shapes, const i
     a.d = mk(bs, cams, num_feat, C, L, A, P, G);
     a.workspace = workspace; a.workspace_bytes = workspace_bytes;
     a.stream = reinterpret_cast<cudaStream_t>(stream);
-    a.stage_mask = stage_mask;
+    a.stage_mask = stage_mask & 7;
+    a.separate_zero_fill = (stage_mask & 8) != 0;
     return launch_backward(a);
 }
 }  // namespace
@@ -124,7 +125,7 @@ int hipad_dfa_backward_stages(int feat_is_bf16, int stage_mask, const void* mc_m
     return backward_common(feat_is_bf16 ? kBF16 : kF32, mc_ms_feat, spatial_shape, scale_start_index, sample_location,
                            weights, grad_output, grad_mc_ms_feat, grad_sampling_location, grad_weights, batch_size,
                            num_cams, num_feat, num_embeds, num_scale, num_anchors, num_pts, num_groups, workspace,
-                           workspace_bytes, stream, stage_mask & 7);
+                           workspace_bytes, stream, stage_mask & 15);
 }
 
 int hipad_dfa_sample_indices(int32_t* indices, const int32_t* spatial_shape, const int32_t* scale_start_index,

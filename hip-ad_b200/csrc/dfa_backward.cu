@@ -9,35 +9,45 @@ constexpr size_t kAlign = 256;
 inline size_t align_up(size_t v) { return (v + kAlign - 1) / kAlign * kAlign; }
 
 struct WorkspaceLayout {
-    size_t rec, seg, counts, sortbuf, heavy_list, heavy_count, total;
-    int seg_stride;
+    size_t vis_id, vis_xy, vis_cnt, rec, seg, cursor, sortbuf, heavy_list, light_list, partial, unit_done, counters, total;
+    size_t partial_slots;
+    int seg_stride, n_chunks;
 };
 
 WorkspaceLayout workspace_layout(const Dims& d) {
     WorkspaceLayout w;
     const size_t n_cl = (size_t)d.cams * d.L, AP = (size_t)d.A * d.P;
-    // sum over (cam,level) of (H+1)(W+1)+1 <= 2*num_feat + 3*cams*L for any shapes with H,W >= 1
-    w.seg_stride = (int)(2 * (size_t)d.num_feat + 3 * n_cl);
+    w.n_chunks = (int)((AP + kVisChunk - 1) / kVisChunk);
+    // band tables of a bucket occupy [8*start, 8*(start + h*w)) (dfa_gfeat.cuh, seg_offset)
+    w.seg_stride = (int)((size_t)kSegScale * d.num_feat);
     size_t off = 0;
-    w.rec = off;     off += align_up((size_t)d.bs * n_cl * AP * sizeof(int));
+    w.vis_id = off;  off += align_up((size_t)d.bs * d.cams * AP * sizeof(int));
+    w.vis_xy = off;  off += align_up((size_t)d.bs * d.cams * AP * sizeof(float2));
+    w.vis_cnt = off; off += align_up((size_t)d.bs * d.cams * w.n_chunks * sizeof(int));
+    w.rec = off;     off += align_up((size_t)d.bs * n_cl * AP * sizeof(int4));
     w.seg = off;     off += align_up((size_t)d.bs * w.seg_stride * sizeof(int));
-    w.counts = off;  off += align_up((size_t)d.bs * n_cl * sizeof(int));
+    w.cursor = off;  off += align_up((size_t)d.bs * n_cl * sizeof(int));
     w.sortbuf = off; off += align_up((size_t)d.bs * n_cl * 2 * AP * sizeof(unsigned long long));
-    w.heavy_list = off;  off += align_up((size_t)d.bs * d.num_feat * sizeof(int2));
-    w.heavy_count = off; off += align_up(sizeof(int));
+    // multi-unit rows: sum of ceil(n/kHeavyUnit) over rows with n > kHeavyUnit <= 2 * (4 * bs*AP*cams*L) / kHeavyUnit
+    w.partial_slots = (size_t)d.bs * AP * n_cl * 8 / kHeavyUnit + 1;
+    w.heavy_list = off;  off += align_up(((size_t)d.bs * d.num_feat + w.partial_slots) * kEntryInts * sizeof(int));
+    w.light_list = off;  off += align_up((size_t)d.bs * d.num_feat * kEntryInts * sizeof(int));
+    w.partial = off;     off += align_up(w.partial_slots * d.C * sizeof(float));
+    w.unit_done = off;   off += align_up(w.partial_slots * sizeof(int));
+    w.counters = off;    off += align_up(4 * sizeof(int));
     w.total = off;
     return w;
 }
 
 template <typename T>
-int launch_reduce(const GfeatParams& gp, KernelShape ks, dim3 grid, cudaStream_t st) {
+int launch_reduce(const GfeatParams& gp, KernelShape ks, cudaStream_t st) {
     constexpr int VV = 16 / (int)sizeof(T);
 #define HIPAD_RED(V_, NCH_)                                                                \
     do {                                                                                   \
-        dfa_gfeat_reduce_kernel<T, V_, NCH_><<<grid, kReduceWarps * 32, 0, st>>>(gp);      \
+        dfa_gfeat_light_kernel<T, V_, NCH_><<<kLightCtas, kLightWarps * 32, 0, st>>>(gp);  \
         cudaError_t e_ = cudaGetLastError();                                               \
         if (e_ != cudaSuccess) return (int)e_;                                             \
-        dfa_gfeat_heavy_kernel<T, V_, NCH_><<<kHeavyCtas, kReduceWarps * 32, 0, st>>>(gp); \
+        dfa_gfeat_heavy_kernel<T, V_, NCH_><<<kHeavyCtas, kHeavyWarps * 32, 0, st>>>(gp);  \
         return (int)cudaGetLastError();                                                    \
     } while (0)
     if (ks.vector) {
@@ -65,13 +75,15 @@ int launch_backward(const BwdArgs& a) {
     const KernelShape ks = pick_shape(a.type, d.C, d.G, al);
     if (!ks.ok || d.cams * d.L > kMaxCamLevels || (long long)d.num_feat * d.C >= (1LL << 30)) return -2;
     const WorkspaceLayout wl = workspace_layout(d);
-    if (a.workspace == nullptr || a.workspace_bytes < wl.total ||
-        reinterpret_cast<uintptr_t>(a.workspace) % kAlign != 0)
+    if (a.g_feat != nullptr &&
+        (a.workspace == nullptr || a.workspace_bytes < wl.total ||
+         reinterpret_cast<uintptr_t>(a.workspace) % kAlign != 0))
         return -3;
-    if ((long long)d.A * d.P > (1LL << 30)) return -2;
-    if ((long long)d.A * d.P * d.cams * d.L * d.G >= (1LL << 31) || (long long)d.A * d.C >= (1LL << 31)) return -2;
+    if ((long long)d.A * d.P > (long long)kMaxChunks * kVisChunk) return -2;
+    // 32-bit BYTE offsets inside one batch element's weights / grad_out (dfa_gfeat.cuh, accumulate_row)
+    if ((long long)d.A * d.P * d.cams * d.L * d.G >= (1LL << 30) || (long long)d.A * d.C >= (1LL << 30)) return -2;
 
-    // ---- K1: sample-major, g_w + g_loc (fully written)
+    // ---- K1: sample-major, g_w + g_loc (fully written); zero-fills g_feat on the side when it has the CTAs
     SampleParams p = {};
     p.feat = a.feat; p.shapes = a.shapes; p.starts = a.starts;
     p.loc = a.loc; p.weights = a.weights;
@@ -79,13 +91,30 @@ int launch_backward(const BwdArgs& a) {
     p.d = d;
     const int NP = d.P * d.cams;
     const long long rows = (long long)d.bs * d.A;
-    p.S = choose_slices(rows, NP, 4 * 148);
+    p.S = choose_slices(rows, NP, 4 * 148, sample_smem_per_pair(kBwd, d.L), /*max_slices=*/1 << 20);
+    if (p.S == 0 || d.bs > 65535 || (long long)d.bs * d.num_feat >= (1LL << 31)) return -2;
     p.PS = (NP + p.S - 1) / p.S;
-    if (p.PS > kMaxPairsPerSlice) return -2;
     const long long grid = rows * p.S;
     if (grid > 0x7fffffffLL) return -2;
     const size_t smem = sample_smem_for(kBwd, d, ks, a.type, p.PS);
+    if (smem > kSampleSmemBudget) return -2;
+    const size_t gfeat_bytes = (size_t)d.bs * d.num_feat * d.C * (a.type == kF32 ? 4 : 2);
     if (a.stage_mask & 1) {
+        if (a.g_feat != nullptr) {
+            const bool vec_ok = (gfeat_bytes % 16 == 0) && (reinterpret_cast<uintptr_t>(a.g_feat) % 16 == 0);
+            if (vec_ok && grid >= 2 * 148 && !a.separate_zero_fill) {
+                p.zero_ptr = reinterpret_cast<uint4*>(a.g_feat);
+                p.zero_n16 = (long long)(gfeat_bytes / 16);
+            } else if (vec_ok) {
+                dfa_zero_kernel<<<148 * 8, 256, 0, a.stream>>>(reinterpret_cast<uint4*>(a.g_feat),
+                                                              (long long)(gfeat_bytes / 16));
+                const cudaError_t e = cudaGetLastError();
+                if (e != cudaSuccess) return (int)e;
+            } else {
+                const cudaError_t e = cudaMemsetAsync(a.g_feat, 0, gfeat_bytes, a.stream);
+                if (e != cudaSuccess) return (int)e;
+            }
+        }
         const int rc = (a.type == kF32)
                            ? dispatch_sample<float, kBwd, false>(p, ks, (int)grid, smem, a.stream)
                            : dispatch_sample<__nv_bfloat16, kBwd, false>(p, ks, (int)grid, smem, a.stream);
@@ -93,38 +122,51 @@ int launch_backward(const BwdArgs& a) {
     }
     if (a.g_feat == nullptr) return 0;   // caller does not need the feature-map gradient
 
-    // ---- K2a: per-(b,cam,level) bucket sort of the visible samples by quad key
+    // ---- K2: visible-sample compaction, then per-(b,cam,level,band) sort by quad key
     unsigned char* ws = reinterpret_cast<unsigned char*>(a.workspace);
     GfeatParams gp = {};
     gp.shapes = a.shapes; gp.starts = a.starts; gp.loc = a.loc; gp.weights = a.weights;
     gp.grad_out = a.grad_out; gp.g_feat = a.g_feat;
-    gp.rec = reinterpret_cast<int*>(ws + wl.rec);
+    gp.vis_id = reinterpret_cast<int*>(ws + wl.vis_id);
+    gp.vis_xy = reinterpret_cast<float2*>(ws + wl.vis_xy);
+    gp.vis_cnt = reinterpret_cast<int*>(ws + wl.vis_cnt);
+    gp.rec = reinterpret_cast<int4*>(ws + wl.rec);
     gp.seg = reinterpret_cast<int*>(ws + wl.seg);
-    gp.counts = reinterpret_cast<int*>(ws + wl.counts);
+    gp.cursor = reinterpret_cast<int*>(ws + wl.cursor);
     gp.sortbuf = reinterpret_cast<unsigned long long*>(ws + wl.sortbuf);
-    gp.heavy_list = reinterpret_cast<int2*>(ws + wl.heavy_list);
-    gp.heavy_count = reinterpret_cast<int*>(ws + wl.heavy_count);
+    gp.heavy_list = reinterpret_cast<int4*>(ws + wl.heavy_list);
+    gp.partial = reinterpret_cast<float*>(ws + wl.partial);
+    gp.unit_done = reinterpret_cast<int*>(ws + wl.unit_done);
+    gp.light_list = reinterpret_cast<int4*>(ws + wl.light_list);
+    gp.counters = reinterpret_cast<int*>(ws + wl.counters);
     gp.d = d;
     gp.seg_stride = wl.seg_stride;
-    const long long AP = (long long)d.A * d.P;
-    int cap = 24576;
-    if (AP < cap) cap = (int)((AP + 63) / 64 * 64);
-    gp.smem_cap = cap;
+    gp.n_chunks = wl.n_chunks;
+    // enough bands for ~2 sort CTAs per SM, whatever the batch size
+    const int buckets = d.cams * d.L * d.bs;
+    int nb = (2 * 148) / buckets;
+    gp.NB = nb < 1 ? 1 : (nb > kMaxBands ? kMaxBands : nb);
     if (a.stage_mask & 2) {
-        const size_t sort_smem = bucket_sort_smem_bytes(cap);
-        cudaError_t e = ensure_smem(dfa_bucket_sort_kernel, sort_smem);
+        dfa_vis_compact_kernel<<<dim3((unsigned)wl.n_chunks, (unsigned)d.cams, (unsigned)d.bs), kVisThreads, 0,
+                                 a.stream>>>(gp);
+        cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return (int)e;
-        dfa_bucket_sort_kernel<<<dim3((unsigned)(d.cams * d.L), (unsigned)d.bs), kSortThreads, sort_smem, a.stream>>>(gp);
+        const size_t sort_smem = band_sort_smem_bytes(wl.n_chunks);
+        e = ensure_smem(dfa_band_sort_kernel, sort_smem);
+        if (e != cudaSuccess) return (int)e;
+        dfa_band_sort_kernel<<<dim3((unsigned)gp.NB, (unsigned)(d.cams * d.L), (unsigned)d.bs), kSortThreads, sort_smem,
+                               a.stream>>>(gp);
         e = cudaGetLastError();
         if (e != cudaSuccess) return (int)e;
     }
     if (!(a.stage_mask & 4)) return 0;
 
-    // ---- K2b: feature-major reduce, writes every row of g_feat once
-    const unsigned tiles = (unsigned)((d.num_feat + kRowsPerTile - 1) / kRowsPerTile + d.cams * d.L);
-    const dim3 rgrid(tiles, (unsigned)d.bs);
-    return (a.type == kF32) ? launch_reduce<float>(gp, ks, rgrid, a.stream)
-                            : launch_reduce<__nv_bfloat16>(gp, ks, rgrid, a.stream);
+    // ---- K3: feature-major reduce, overwrites every touched row of the zero-filled g_feat once
+    dfa_row_classify_kernel<<<dim3((unsigned)((d.num_feat + kClassifyThreads - 1) / kClassifyThreads), (unsigned)d.bs),
+                              kClassifyThreads, 0, a.stream>>>(gp);
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return (int)e;
+    return (a.type == kF32) ? launch_reduce<float>(gp, ks, a.stream) : launch_reduce<__nv_bfloat16>(gp, ks, a.stream);
 }
 
 }  // namespace hipad

@@ -6,7 +6,12 @@
 namespace hipad {
 
 constexpr int kSampleWarps = 8;
-constexpr int kMaxPairsPerSlice = 8192;
+constexpr size_t kSampleSmemBudget = 220 * 1024;   // dynamic shared memory one sample-kernel CTA may ask for
+
+// shared-memory bytes of gather metadata per (p,cam) pair of a slice (sample_smem_layout, dfa_sample.cuh)
+inline int sample_smem_per_pair(int mode, int L) {
+    return 8 + 4 + L * (16 + 16 + 4) + (mode == kBwd ? 1 + L * 32 : 0);
+}
 
 template <typename K>
 inline cudaError_t ensure_smem(K kern, size_t smem) {

@@ -23,10 +23,15 @@ KernelShape pick_shape(ElemType t, int C, int G, bool aligned16) {
     return ks;
 }
 
-int choose_slices(long long rows, int pairs, int target_ctas) {
+int choose_slices(long long rows, int pairs, int target_ctas, int bytes_per_pair, int max_slices) {
     int S = 1;
-    while (S < 8 && rows * S < target_ctas && pairs / (S * 2) >= 64) S *= 2;
-    while (S < 8 && (pairs + S - 1) / S > kMaxPairsPerSlice) S *= 2;
+    while (S < 8 && S * 2 <= max_slices && rows * S < target_ctas && pairs / (S * 2) >= 64) S *= 2;
+    // fixed part of the CTA's shared memory (tables, reduction scratch) is < 48 KB for every supported shape
+    const long long budget = (long long)kSampleSmemBudget - 48 * 1024;
+    while ((long long)((pairs + S - 1) / S) * bytes_per_pair > budget) {
+        if (S * 2 > max_slices) return 0;
+        S *= 2;
+    }
     return S;
 }
 
@@ -46,12 +51,13 @@ int launch_forward(const FwdArgs& a) {
     p.d = d;
     const int NP = d.P * d.cams;
     const long long rows = (long long)d.bs * d.A;
-    p.S = choose_slices(rows, NP, 4 * 148);
+    p.S = choose_slices(rows, NP, 4 * 148, sample_smem_per_pair(mode, d.L), /*max_slices=*/8);   // cluster size <= 8
+    if (p.S == 0) return -2;
     p.PS = (NP + p.S - 1) / p.S;
-    if (p.PS > kMaxPairsPerSlice) return -2;
     const long long grid = rows * p.S;
     if (grid > 0x7fffffffLL) return -2;
     const size_t smem = sample_smem_for(mode, d, ks, a.type, p.PS);
+    if (smem > kSampleSmemBudget) return -2;
 
 #define HIPAD_GO(T_, MODE_)                                                                  \
     return (p.S > 1) ? dispatch_sample<T_, MODE_, true>(p, ks, (int)grid, smem, a.stream)    \

@@ -1,35 +1,57 @@
 // dfa_gfeat.cuh — deterministic feature-map gradient (the scatter half of cu:62-126).
 //
-// The reference scatters 4 fp32 atomicAdds per (sample, level, channel) into grad_mc_ms_feat.
-// Here the scatter is turned into a gather, so every feature row is written exactly once,
-// in a fixed summation order, with zeros for untouched rows (no memset, no atomics):
+// The reference scatters 4 fp32 atomicAdds per (sample, level, channel) into a pre-zeroed
+// grad_mc_ms_feat.  Here the scatter is turned into a gather, every touched feature row is summed in a
+// fixed order and written once, and no floating-point atomic exists:
 //
-//   dfa_bucket_sort_kernel   one CTA per (b, cam, level) "bucket".  Scans the bucket's samples
-//       in canonical order, compacts the visible ones, computes the PADDED quad key
-//       (h_low+1)*(W+1) + (w_low+1) of each, and radix-sorts (key, sample) words inside shared
-//       memory (stable LSD passes built on __match_any_sync; global-memory ping-pong only if a
-//       bucket exceeds the 227 KB CTA budget).  Emits the sorted sample ids and a dense
-//       segment table seg[key] = first sorted position with key' >= key.
-//   dfa_gfeat_reduce_kernel  one warp per feature row.  A row (y,x) is corner 1/2/3/4 of the
-//       quads keyed (y,x), (y,x-1), (y-1,x), (y-1,x-1): four segments of the table.  The warp
-//       walks them in order, re-derives the bilinear coefficient from the sample location with
-//       the same quad_setup() as the forward, and accumulates coef * w[g] * grad_out[b,a,:]
-//       in registers (lane = V channels x NCH chunks, LDG.128 coalesced).  Rows with many
-//       contributions (coarse levels) are split across the CTA's warps and combined in fixed
-//       order through shared memory.  Coarse levels are scheduled first (longest work first).
+//   dfa_zero_kernel         dense zero fill of grad_mc_ms_feat (streaming 16-byte stores).  When the
+//       sample-major backward kernel has enough CTAs the fill is folded into that kernel instead (its
+//       stores ride under the gather latency of that kernel, which leaves the HBM write path idle).
+//   dfa_vis_compact_kernel  per (b, cam, chunk of 1024 samples): ordered compaction of the visible
+//       samples (id + location).  Many small CTAs; the only pass that touches every location.
+//   dfa_band_sort_kernel    per (b, cam, level, BAND of quad rows): picks the visible samples whose quad
+//       falls into its band (ordered), radix-sorts (quad key, sample) words in shared memory (stable LSD,
+//       __match_any_sync ranks), and emits 16-byte records {sample, anchor, lh, lw} in sorted order plus
+//       the band's segment table seg[key] = first record with key' >= key.  A (cam, level) bucket is
+//       split into up to 16 bands so that ~2 CTAs per SM run even at batch size 1 (the previous
+//       one-CTA-per-bucket sort left 124 of 148 SMs idle).  Where a band's records land inside the
+//       bucket's record array is decided by an integer atomic cursor; the order INSIDE a key segment is
+//       the stable sample order, which is all the summation order depends on.
+//   dfa_row_classify_kernel one thread per feature row: 4 segment lookups (row (y,x) is corner 1/2/3/4 of
+//       the quads keyed (y,x), (y,x-1), (y-1,x), (y-1,x-1)); rows with 1..kHeavyRow contributions are
+//       appended (warp-aggregated integer atomics) to the LIGHT work list together with their segment
+//       bounds, rows with more to the HEAVY list.  Untouched rows (most of them) cost a few loads.
+//   dfa_gfeat_light_kernel  persistent warps stride over the light list; one warp per row accumulates
+//       coef * w[g] * grad_out[b,a,:] in registers (lane = V channels x NCH chunks, LDG.128) in the
+//       row's fixed order and overwrites the row.  List order is irrelevant for the result (each row is
+//       summed by one warp in sorted-record order) and the stride interleaves coarse and fine levels, so
+//       the load is balanced at warp granularity.
+//   dfa_gfeat_heavy_kernel  rows with > kHeavyRow contributions (coarse levels): persistent CTAs whose
+//       8 warps split one row's contributions into contiguous ranges and combine the partials in warp
+//       order.
 #pragma once
 #include "dfa_common.cuh"
 
 namespace hipad {
 
-constexpr int kSortThreads = 1024;
+constexpr int kVisChunk = 1024;          // samples per compaction chunk
+constexpr int kVisThreads = 256;
+constexpr int kSortThreads = 512;
 constexpr int kSortWarps = kSortThreads / 32;
 constexpr int kRadixBits = 8;
 constexpr int kRadix = 1 << kRadixBits;
-constexpr int kReduceWarps = 8;
-constexpr int kRowsPerTile = 32;         // rows of one (cam, level) per CTA
-constexpr int kHeavyRow = 64;
-constexpr int kHeavyCtas = 148 * 6;      // persistent CTAs of the heavy-row kernel   // contributions above which a row is split across the CTA
+constexpr int kBandCap = 8192;           // packed words per ping-pong half kept in shared memory
+constexpr int kMaxBands = 16;
+constexpr int kScanUnroll = 8;           // independent loads in flight per lane in the band kernel's scans
+constexpr int kSegScale = 8;             // ints of segment table per feature row (upper bound, see seg_offset)
+constexpr int kClassifyThreads = 256;    // rows classified per CTA (one thread each)
+constexpr int kLightWarps = 8;
+constexpr int kLightCtas = 148 * 4;      // persistent CTAs of the light-row kernel
+constexpr int kHeavyWarps = 8;
+constexpr int kHeavyRow = 64;            // contributions above which a row goes to the heavy kernel
+constexpr int kHeavyUnit = 512;          // contributions per heavy work unit (one CTA pass)
+constexpr int kHeavyCtas = 148 * 2;      // persistent CTAs of the heavy-row kernel
+constexpr int kMaxChunks = 4096;         // A*P <= 4 Mi samples per batch element
 
 struct GfeatParams {
     const int* shapes;
@@ -38,15 +60,22 @@ struct GfeatParams {
     const float* weights;
     const float* grad_out;
     void* g_feat;
-    int* rec;        // [bs][cams*L][A*P]   sorted sample ids (a*P + p)
-    int* seg;        // [bs][seg_stride]    per bucket: (H+1)(W+1)+1 entries
-    int* counts;     // [bs][cams*L]        visible samples per bucket
-    unsigned long long* sortbuf;  // [bs][cams*L][2][A*P] global ping-pong (large buckets only)
-    int2* heavy_list;  // [bs*num_feat] rows with > kHeavyRow contributions: (b*cams*L + cl, row in level)
-    int* heavy_count;  // zeroed by the bucket-sort kernel
+    int* vis_id;       // [bs][cams][A*P]      compacted visible sample ids, chunk c at [c*kVisChunk, ...)
+    float2* vis_xy;    // [bs][cams][A*P]      their locations
+    int* vis_cnt;      // [bs][cams][n_chunks] visible samples per chunk
+    int4* rec;         // [bs][cams*L][A*P]    sorted records {sample, anchor, lh, lw}
+    int* seg;          // [bs][seg_stride]     segment tables (absolute positions inside the bucket's rec[])
+    int* cursor;       // [bs][cams*L]         records allocated so far in each bucket
+    unsigned long long* sortbuf;  // [bs][cams*L][2][A*P] global ping-pong (bands that exceed shared memory)
+    int4* heavy_list;  // [bs*num_feat + partial slots][4]  work-list entries (kEntryInts), one per heavy unit
+    int4* light_list;  // [bs*num_feat][4]                  work-list entries, one per light row
+    float* partial;    // [partial slots][C]   unit sums of rows with more than one unit
+    int* unit_done;    // [partial slots]      units finished, indexed by a row's first slot
+    int* counters;     // [0] heavy units  [1] light rows  [2] partial slots   (zeroed by the compaction kernel)
     Dims d;
-    int seg_stride;  // ints per batch element in seg
-    int smem_cap;    // words of packed records that fit in shared memory (per ping-pong half)
+    int seg_stride;    // ints per batch element in seg
+    int n_chunks;
+    int NB;            // requested bands per bucket (<= kMaxBands)
 };
 
 __host__ __device__ inline int bits_for(unsigned v) {   // number of bits to represent values < v
@@ -55,11 +84,88 @@ __host__ __device__ inline int bits_for(unsigned v) {   // number of bits to rep
     return b;
 }
 
-// Stable LSD radix sort of n packed words on bits [lo_bit, lo_bit + nbits) by one CTA.
+// Band geometry of a (cam, level) bucket of h x w pixels.  Quads are keyed in PADDED coordinates
+// (h_low+1, w_low+1) in [0,h] x [0,w]; band j owns padded quad rows [j*RB, (j+1)*RB).
+struct Bands {
+    int nb, RB, row_keys, tab;   // bands, quad rows per band, keys per quad row (w+1), ints per band table
+};
+__device__ __forceinline__ Bands band_geometry(int h, int w, int NB) {
+    Bands g;
+    g.nb = min(NB, h + 1);
+    g.RB = (h + 1 + g.nb - 1) / g.nb;
+    g.row_keys = w + 1;
+    g.tab = g.RB * g.row_keys + 1;       // + sentinel
+    return g;
+}
+// Segment tables of bucket `cl` start at kSegScale * start[cl]:  nb*tab <= (2h+1)(w+1) + h + 1 <= 8*h*w,
+// so buckets whose row ranges are disjoint never overlap, whatever their order.
+__device__ __forceinline__ size_t seg_offset(int start) { return (size_t)kSegScale * (size_t)start; }
+
+// ------------------------------------------------------------------------------------------ zero fill
+__global__ void __launch_bounds__(256) dfa_zero_kernel(uint4* __restrict__ dst, long long n16) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) dst[i] = z;
+}
+
+// ------------------------------------------------------------------------------------------ compaction
+// grid (n_chunks, cams, bs), block kVisThreads.  Warp w of chunk c owns samples
+// [c*kVisChunk + w*128, +128): ordered inside the chunk, chunks are concatenated by the consumers.
+__global__ void __launch_bounds__(kVisThreads) dfa_vis_compact_kernel(const GfeatParams p) {
+    constexpr int kWarps = kVisThreads / 32;
+    constexpr int kPerWarp = kVisChunk / kWarps;     // 128
+    constexpr int kIter = kPerWarp / 32;             // 4
+    const Dims d = p.d;
+    const int c = blockIdx.x, cam = blockIdx.y, b_idx = blockIdx.z;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int AP = d.A * d.P;
+    __shared__ int s_wcnt[kWarps];
+
+    if (c == 0 && cam == 0) {
+        for (int i = tid; i < d.cams * d.L; i += kVisThreads) p.cursor[(size_t)b_idx * d.cams * d.L + i] = 0;
+        if (b_idx == 0 && tid < 4) p.counters[tid] = 0;
+    }
+    const float2* loc2 = reinterpret_cast<const float2*>(p.loc) + (size_t)b_idx * AP * d.cams + cam;
+    const int s_base = c * kVisChunk + warp * kPerWarp;
+    float2 xy[kIter];
+    unsigned bal[kIter];
+    int cnt = 0;
+#pragma unroll
+    for (int it = 0; it < kIter; ++it) {
+        const int s = s_base + it * 32 + lane;
+        xy[it] = make_float2(-1.f, -1.f);
+        if (s < AP) xy[it] = __ldg(loc2 + (size_t)s * d.cams);
+        bal[it] = __ballot_sync(0xffffffffu, loc_valid(xy[it].x, xy[it].y));
+        cnt += __popc(bal[it]);
+    }
+    if (lane == 0) s_wcnt[warp] = cnt;
+    __syncthreads();
+    int pos = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) {
+        const int n = s_wcnt[w];
+        if (w < warp) pos += n;
+        total += n;
+    }
+    const size_t list = ((size_t)b_idx * d.cams + cam) * AP + (size_t)c * kVisChunk;
+#pragma unroll
+    for (int it = 0; it < kIter; ++it) {
+        if ((bal[it] >> lane) & 1u) {
+            const int at = pos + __popc(bal[it] & ((1u << lane) - 1u));
+            p.vis_id[list + at] = s_base + it * 32 + lane;
+            p.vis_xy[list + at] = xy[it];
+        }
+        pos += __popc(bal[it]);
+    }
+    if (tid == 0) p.vis_cnt[((size_t)b_idx * d.cams + cam) * p.n_chunks + c] = total;
+}
+
+// ------------------------------------------------------------------------------------------ band sort
+// Stable LSD radix sort of n packed words on bits [lo_bit, lo_bit + nbits) by one CTA of kSortThreads.
 // a/b: ping-pong arrays (shared or global).  Returns the array holding the result.
 template <typename W>
 __device__ W* block_radix_sort(W* a, W* b, int n, int lo_bit, int nbits, unsigned* hist /*[kSortWarps][kRadix]*/,
-                               unsigned* tot /*[kRadix]*/) {
+                               unsigned* tot /*[kRadix + 32]*/) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     int chunk = (n + kSortWarps - 1) / kSortWarps;
     chunk = (chunk + 31) & ~31;
@@ -79,6 +185,7 @@ __device__ W* block_radix_sort(W* a, W* b, int n, int lo_bit, int nbits, unsigne
         __syncthreads();
         if (tid < kRadix) {
             unsigned run = 0;
+#pragma unroll
             for (int w = 0; w < kSortWarps; ++w) {
                 const unsigned c = hist[w * kRadix + tid];
                 hist[w * kRadix + tid] = run;
@@ -95,12 +202,13 @@ __device__ W* block_radix_sort(W* a, W* b, int n, int lo_bit, int nbits, unsigne
                 const unsigned t = __shfl_up_sync(0xffffffffu, inc, o);
                 if (lane >= o) inc += t;
             }
-            if (lane == 31) tot[kRadix + warp] = inc;     // tot has kRadix + 32 entries
+            if (lane == 31) tot[kRadix + warp] = inc;
             __syncwarp();
             asm volatile("bar.sync 1, 256;");              // only the first 8 warps take part
             unsigned base = 0;
             for (int ww = 0; ww < warp; ++ww) base += tot[kRadix + ww];
             base += inc - mine;
+#pragma unroll
             for (int w = 0; w < kSortWarps; ++w) hist[w * kRadix + tid] += base;
         }
         __syncthreads();
@@ -128,239 +236,341 @@ __device__ W* block_radix_sort(W* a, W* b, int n, int lo_bit, int nbits, unsigne
     return a;
 }
 
-// exclusive scan of kSortWarps (=32) per-warp counts by warp 0; returns total via smem
-__device__ __forceinline__ void scan_warp_counts(int* s_wcnt /*[32] in: counts, out: exclusive offsets*/, int* s_total) {
-    if (threadIdx.x < 32) {
-        const int lane = threadIdx.x;
-        const int c = s_wcnt[lane];
-        int inc = c;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int t = __shfl_up_sync(0xffffffffu, inc, o);
-            if (lane >= o) inc += t;
-        }
-        s_wcnt[lane] = inc - c;
-        if (lane == 31) *s_total = inc;
-    }
-}
+struct BandCtx {
+    int b_idx, cam, cl, h, w, q0, q1, K, n, base, vb, kb;
+    const int* s_coff;    // per chunk: offset of its first in-band sample inside the band's list
+};
 
+// compaction (chunk order, then order inside the chunk) + sort + record/segment emission of one band
 template <typename W>
-__device__ void bucket_sort_body(const GfeatParams& p, W* a, W* b, unsigned* hist, unsigned* tot, const int* s_woff,
-                                 int n, int b_idx, int cam, int cl, int h, int w, int segoff) {
+__device__ void band_sort_body(const GfeatParams& p, const BandCtx& bc, W* a, W* b, unsigned* hist, unsigned* tot,
+                               int* seg_band) {
     const Dims d = p.d;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int AP = d.A * d.P;
-    const int vb = bits_for((unsigned)AP);
-    const int K = (h + 1) * (w + 1);
-    const int kb = bits_for((unsigned)K);
-    const float2* loc2 = reinterpret_cast<const float2*>(p.loc) + (size_t)b_idx * AP * d.cams + cam;
+    const size_t cam_list = ((size_t)bc.b_idx * d.cams + bc.cam) * AP;
+    const int* cnts = p.vis_cnt + ((size_t)bc.b_idx * d.cams + bc.cam) * p.n_chunks;
 
-    // ordered compaction: warp `warp` owns the contiguous sample range [beg, end) and writes its
-    // visible samples at s_woff[warp] + running rank -> canonical (sample-index) order overall.
-    int chunk = (AP + kSortWarps - 1) / kSortWarps;
-    chunk = (chunk + 31) & ~31;
-    const int beg = min(AP, warp * chunk), end = min(AP, beg + chunk);
-    int pos = s_woff[warp];
-    for (int s0 = beg; s0 < end; s0 += 32) {
-        const int s = s0 + lane;
-        bool vis = false;
-        W word = 0;
-        if (s < end) {
-            const float2 xy = __ldg(loc2 + (size_t)s * d.cams);
-            vis = loc_valid(xy.x, xy.y);
-            if (vis) {
-                const Quad q = quad_setup(xy.x, xy.y, h, w);
-                const unsigned key = (unsigned)((q.h_low + 1) * (w + 1) + (q.w_low + 1));
-                word = ((W)key << vb) | (W)s;
+    for (int c = warp; c < p.n_chunks; c += kSortWarps) {
+        const int cnt = __ldg(cnts + c);
+        const int* ids = p.vis_id + cam_list + (size_t)c * kVisChunk;
+        const float2* xys = p.vis_xy + cam_list + (size_t)c * kVisChunk;
+        int pos = bc.s_coff[c];
+        for (int i0 = 0; i0 < cnt; i0 += 32 * kScanUnroll) {
+            float2 xy[kScanUnroll];
+            int id[kScanUnroll];
+#pragma unroll
+            for (int u = 0; u < kScanUnroll; ++u) {
+                const int i = i0 + u * 32 + lane;
+                xy[u] = make_float2(-1.f, -1.f);
+                id[u] = 0;
+                if (i < cnt) {
+                    xy[u] = __ldg(xys + i);
+                    id[u] = __ldg(ids + i);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < kScanUnroll; ++u) {
+                if (i0 + u * 32 >= cnt) break;   // warp-uniform
+                const Quad q = quad_setup(xy[u].x, xy[u].y, bc.h, bc.w);
+                const int qr = q.h_low + 1;
+                const bool in = (i0 + u * 32 + lane < cnt) && qr >= bc.q0 && qr < bc.q1;
+                const unsigned bal = __ballot_sync(0xffffffffu, in);
+                if (in) {
+                    const unsigned key = (unsigned)((qr - bc.q0) * (bc.w + 1) + (q.w_low + 1));
+                    a[pos + __popc(bal & ((1u << lane) - 1u))] = ((W)key << bc.vb) | (W)id[u];
+                }
+                pos += __popc(bal);
             }
         }
-        const unsigned bal = __ballot_sync(0xffffffffu, vis);
-        if (vis) a[pos + __popc(bal & ((1u << lane) - 1u))] = word;
-        pos += __popc(bal);
     }
     __syncthreads();
 
-    W* sorted = block_radix_sort<W>(a, b, n, vb, kb, hist, tot);
+    W* sorted = block_radix_sort<W>(a, b, bc.n, bc.vb, bc.kb, hist, tot);
 
-    int* rec = p.rec + ((size_t)b_idx * d.cams * d.L + cl) * AP;
-    const W vmask = ((W)1 << vb) - 1;
-    for (int i = tid; i < n; i += kSortThreads) rec[i] = (int)(sorted[i] & vmask);
+    // sorted records: everything the reduce needs per contribution, so it never re-derives the quad
+    int4* rec = p.rec + ((size_t)bc.b_idx * d.cams * d.L + bc.cl) * AP + bc.base;
+    const float2* loc2 = reinterpret_cast<const float2*>(p.loc) + (size_t)bc.b_idx * AP * d.cams + bc.cam;
+    const W vmask = ((W)1 << bc.vb) - 1;
+    for (int i0 = 0; i0 < bc.n; i0 += kSortThreads * 4) {
+        int sid[4];
+        float2 xy[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * kSortThreads + tid;
+            sid[u] = (i < bc.n) ? (int)(sorted[i] & vmask) : 0;
+            xy[u] = __ldg(loc2 + (size_t)sid[u] * d.cams);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * kSortThreads + tid;
+            if (i < bc.n) {
+                const Quad q = quad_setup(xy[u].x, xy[u].y, bc.h, bc.w);
+                rec[i] = make_int4(sid[u], sid[u] / d.P, __float_as_int(q.lh), __float_as_int(q.lw));
+            }
+        }
+    }
 
-    // seg[k] = first sorted position whose key >= k, for k = 0..K:
-    //   fill with n, mark segment starts, then a suffix-min scan closes the gaps of empty keys.
-    int* seg = p.seg + (size_t)b_idx * p.seg_stride + segoff;
-    for (int k = tid; k <= K; k += kSortThreads) seg[k] = n;
+    // seg[k] = first record (absolute position in the bucket) whose key >= k, k = 0..K (K = sentinel):
+    //   fill with the end, mark segment starts, then a suffix-min scan closes the gaps of empty keys.
+    const int end_pos = bc.base + bc.n;
+    for (int k = tid; k <= bc.K; k += kSortThreads) seg_band[k] = end_pos;
     __syncthreads();
-    for (int i = tid; i < n; i += kSortThreads) {
-        const unsigned key = (unsigned)(sorted[i] >> vb);
-        if (i == 0 || (unsigned)(sorted[i - 1] >> vb) != key) seg[key] = i;
+    for (int i = tid; i < bc.n; i += kSortThreads) {
+        const unsigned key = (unsigned)(sorted[i] >> bc.vb);
+        if (i == 0 || (unsigned)(sorted[i - 1] >> bc.vb) != key) seg_band[key] = bc.base + i;
     }
     __syncthreads();
     {
-        const int per = (K + 1 + kSortThreads - 1) / kSortThreads;
-        const int lo = min(K + 1, tid * per), hi = min(K + 1, lo + per);
+        const int per = (bc.K + 1 + kSortThreads - 1) / kSortThreads;
+        const int lo = min(bc.K + 1, tid * per), hi = min(bc.K + 1, lo + per);
         int run = 0x7fffffff;
-        for (int k = hi - 1; k >= lo; --k) run = min(run, seg[k]);
-        // exclusive suffix-min across threads (thread t needs min over threads > t)
-        int v = run;
+        for (int k = hi - 1; k >= lo; --k) run = min(run, seg_band[k]);
+        int v = run;   // inclusive suffix-min over the lanes of this warp
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const int t = __shfl_down_sync(0xffffffffu, v, o);
             if (lane + o < 32) v = min(v, t);
         }
-        int* s_wmin = reinterpret_cast<int*>(tot);          // 32 ints of scratch
+        int* s_wmin = reinterpret_cast<int*>(tot);          // kSortWarps ints of scratch
         __syncthreads();
         if (lane == 0) s_wmin[warp] = v;
         __syncthreads();
         int after = 0x7fffffff;                             // min over later warps
         for (int ww = warp + 1; ww < kSortWarps; ++ww) after = min(after, s_wmin[ww]);
-        int excl = __shfl_down_sync(0xffffffffu, v, 1);     // inclusive suffix-min of lanes > lane
+        int excl = __shfl_down_sync(0xffffffffu, v, 1);     // suffix-min of the lanes after this one
         if (lane == 31) excl = 0x7fffffff;
         int carry = min(excl, after);
         for (int k = hi - 1; k >= lo; --k) {
-            carry = min(carry, seg[k]);
-            seg[k] = carry;
+            carry = min(carry, seg_band[k]);
+            seg_band[k] = carry;
         }
     }
-    if (tid == 0) p.counts[(size_t)b_idx * d.cams * d.L + cl] = n;
 }
 
-// grid (cams*L, bs), block kSortThreads, dynamic smem = hist + tot + counters + 2*smem_cap words
-__global__ void __launch_bounds__(kSortThreads) dfa_bucket_sort_kernel(const GfeatParams p) {
-    const Dims d = p.d;
-    const int cl = blockIdx.x, b_idx = blockIdx.y;
-    const int cam = cl / d.L;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    unsigned* hist = reinterpret_cast<unsigned*>(smem_raw);
-    unsigned* tot = hist + kSortWarps * kRadix;            // kRadix totals + 32 scratch
-    int* s_wcnt = reinterpret_cast<int*>(tot + kRadix + 32);
-    int* s_misc = s_wcnt + kSortWarps;           // [0] segoff  [1] visible count of (b,cam)
-    unsigned char* data = reinterpret_cast<unsigned char*>(s_misc + 16);
+// dynamic smem: hist[kSortWarps*kRadix] + tot[kRadix+32] + misc[16] + coff[n_chunks] + 2*kBandCap words
+inline size_t band_sort_smem_bytes(int n_chunks) {
+    return (size_t)(kSortWarps * kRadix + kRadix + 32 + 16 + ((n_chunks + 3) & ~3)) * 4 + (size_t)kBandCap * 2 * 4;
+}
 
+// grid (NB, cams*L, bs), block kSortThreads
+__global__ void __launch_bounds__(kSortThreads) dfa_band_sort_kernel(const GfeatParams p) {
+    const Dims d = p.d;
+    const int band = blockIdx.x, cl = blockIdx.y, b_idx = blockIdx.z;
+    const int cam = cl / d.L;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int AP = d.A * d.P;
-    if (blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) *p.heavy_count = 0;
-    if (warp == 0) {
-        int off = 0;
-        for (int i = lane; i < cl; i += 32)
-            off += (__ldg(p.shapes + i * 2) + 1) * (__ldg(p.shapes + i * 2 + 1) + 1) + 1;
-        off = __reduce_add_sync(0xffffffffu, off);
-        if (lane == 0) s_misc[0] = off;
-    }
-    // per-warp visible counts over the same contiguous ranges the compaction pass will use
-    {
-        const float2* loc2 = reinterpret_cast<const float2*>(p.loc) + (size_t)b_idx * AP * d.cams + cam;
-        int chunk = (AP + kSortWarps - 1) / kSortWarps;
-        chunk = (chunk + 31) & ~31;
-        const int beg = min(AP, warp * chunk), end = min(AP, beg + chunk);
-        int c = 0;
-#pragma unroll 8
-        for (int s = beg + lane; s < end; s += 32) {
-            const float2 xy = __ldg(loc2 + (size_t)s * d.cams);
-            c += loc_valid(xy.x, xy.y) ? 1 : 0;
-        }
-        c = __reduce_add_sync(0xffffffffu, c);
-        if (lane == 0) s_wcnt[warp] = c;
-    }
-    __syncthreads();
-    scan_warp_counts(s_wcnt, &s_misc[1]);
-    __syncthreads();
-    const int n_vis = s_misc[1];
-    const int segoff = s_misc[0];
     const int h = __ldg(p.shapes + cl * 2), w = __ldg(p.shapes + cl * 2 + 1);
-    const int bits = bits_for((unsigned)AP) + bits_for((unsigned)((h + 1) * (w + 1)));
+    const Bands g = band_geometry(h, w, p.NB);
+    if (band >= g.nb) return;
+    BandCtx bc;
+    bc.b_idx = b_idx; bc.cam = cam; bc.cl = cl; bc.h = h; bc.w = w;
+    bc.q0 = band * g.RB;
+    bc.q1 = min(h + 1, bc.q0 + g.RB);
+    if (bc.q0 >= bc.q1) return;        // no quad row maps to this band, nobody reads its table
+    bc.K = (bc.q1 - bc.q0) * g.row_keys;
+    bc.vb = bits_for((unsigned)AP);
+    bc.kb = bits_for((unsigned)bc.K);
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    unsigned* hist = reinterpret_cast<unsigned*>(smem_raw);
+    unsigned* tot = hist + kSortWarps * kRadix;
+    int* s_misc = reinterpret_cast<int*>(tot + kRadix + 32);     // [0] n  [1] base
+    int* s_coff = s_misc + 16;
+    unsigned char* data = reinterpret_cast<unsigned char*>(s_coff + ((p.n_chunks + 3) & ~3));
+
+    // in-band samples per chunk (same quad_setup as every other kernel)
+    const size_t cam_list = ((size_t)b_idx * d.cams + cam) * AP;
+    const int* cnts = p.vis_cnt + ((size_t)b_idx * d.cams + cam) * p.n_chunks;
+    for (int c = warp; c < p.n_chunks; c += kSortWarps) {
+        const int cnt = __ldg(cnts + c);
+        const float2* xys = p.vis_xy + cam_list + (size_t)c * kVisChunk;
+        int m = 0;
+        for (int i0 = 0; i0 < cnt; i0 += 32 * kScanUnroll) {   // kScanUnroll independent loads in flight per lane
+            float y[kScanUnroll];
+#pragma unroll
+            for (int u = 0; u < kScanUnroll; ++u) {
+                const int i = i0 + u * 32 + lane;
+                y[u] = (i < cnt) ? __ldg(reinterpret_cast<const float*>(xys + i) + 1) : -1.f;   // -1: never in a band
+            }
+#pragma unroll
+            for (int u = 0; u < kScanUnroll; ++u) {
+                const int qr = __float2int_rd(__fmaf_rn(y[u], (float)h, -0.5f)) + 1;
+                m += (qr >= bc.q0 && qr < bc.q1) ? 1 : 0;
+            }
+        }
+        m = __reduce_add_sync(0xffffffffu, m);
+        if (lane == 0) s_coff[c] = m;
+    }
+    __syncthreads();
+    if (warp == 0) {    // exclusive scan over the chunks
+        int run = 0;
+        for (int c0 = 0; c0 < p.n_chunks; c0 += 32) {
+            const int c = c0 + lane;
+            const int m = (c < p.n_chunks) ? s_coff[c] : 0;
+            int inc = m;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += t;
+            }
+            if (c < p.n_chunks) s_coff[c] = run + inc - m;
+            run += __shfl_sync(0xffffffffu, inc, 31);
+        }
+        if (lane == 0) {
+            s_misc[0] = run;
+            s_misc[1] = atomicAdd(p.cursor + (size_t)b_idx * d.cams * d.L + cl, run);
+        }
+    }
+    __syncthreads();
+    bc.n = s_misc[0];
+    bc.base = s_misc[1];
+    bc.s_coff = s_coff;
+
+    int* seg_band = p.seg + (size_t)b_idx * p.seg_stride + seg_offset(__ldg(p.starts + cl)) + (size_t)band * g.tab;
+    // bands that overflow shared memory sort in their slice [base, base+n) of the bucket's global buffers
     unsigned long long* gbuf = p.sortbuf + ((size_t)b_idx * d.cams * d.L + cl) * 2 * AP;
-    if (bits <= 32) {
-        if (n_vis <= p.smem_cap) {
+    if (bc.vb + bc.kb <= 32) {
+        if (bc.n <= kBandCap) {
             unsigned* a = reinterpret_cast<unsigned*>(data);
-            bucket_sort_body<unsigned>(p, a, a + p.smem_cap, hist, tot, s_wcnt, n_vis, b_idx, cam, cl, h, w, segoff);
+            band_sort_body<unsigned>(p, bc, a, a + kBandCap, hist, tot, seg_band);
         } else {
-            unsigned* a = reinterpret_cast<unsigned*>(gbuf);
-            bucket_sort_body<unsigned>(p, a, a + AP, hist, tot, s_wcnt, n_vis, b_idx, cam, cl, h, w, segoff);
+            unsigned* a = reinterpret_cast<unsigned*>(gbuf) + bc.base;
+            band_sort_body<unsigned>(p, bc, a, a + AP, hist, tot, seg_band);
         }
     } else {
-        if (n_vis <= p.smem_cap / 2) {
+        if (bc.n <= kBandCap / 2) {
             unsigned long long* a = reinterpret_cast<unsigned long long*>(data);
-            bucket_sort_body<unsigned long long>(p, a, a + p.smem_cap / 2, hist, tot, s_wcnt, n_vis, b_idx, cam, cl, h, w,
-                                                 segoff);
+            band_sort_body<unsigned long long>(p, bc, a, a + kBandCap / 2, hist, tot, seg_band);
         } else {
-            bucket_sort_body<unsigned long long>(p, gbuf, gbuf + AP, hist, tot, s_wcnt, n_vis, b_idx, cam, cl, h, w,
-                                                 segoff);
+            band_sort_body<unsigned long long>(p, bc, gbuf + bc.base, gbuf + AP + bc.base, hist, tot, seg_band);
         }
     }
 }
 
-inline size_t bucket_sort_smem_bytes(int smem_cap) {
-    return (size_t)(kSortWarps * kRadix + kRadix + 32 + kSortWarps + 16) * 4 + (size_t)smem_cap * 2 * 4;
-}
+// ------------------------------------------------------------------------------------------ reduce
+constexpr int kEntryInts = 16;   // work-list entry, shared by the light and the heavy list:
+//   [0] b*num_feat + row   [1] n (contributions)   [2] b   [3] cam | level << 8 | bucket << 16
+//   [4..7] beg[4]          [8..10] e1, e2, e3      [12] unit | units << 16   [13] first partial slot
 
-// ---------------------------------------------------------------------------------------------
-// Feature-major reduce.  Two kernels:
-//   dfa_gfeat_reduce_kernel  grid (tiles_upper_bound, bs): tile = kRowsPerTile consecutive rows of one
-//       (cam, level), coarsest level first.  One warp per row; rows with more than kHeavyRow
-//       contributions are only APPENDED to a device work list (which CTA ends up processing such a row
-//       is irrelevant for determinism: the summation order inside a row is fixed).
-//   dfa_gfeat_heavy_kernel   persistent CTAs walk that list; the 8 warps of a CTA split one row's
-//       contributions into contiguous ranges and combine the partials in warp order.
 template <int V, int NCH>
 struct RowCtx {
-    const int* rec;        // sorted sample ids of the bucket
-    const float2* loc2;    // locations of (b, :, :, cam)
-    const float* wts;      // weights of (b, :, :, cam, l, :)
-    const float* gout;     // grad_out of batch element b
-    int h, w, cams, P, C, w_stride;
-    int beg[4];            // begin of corner-1/2/3/4 segments in rec[]
-    int e1, e2, e3;        // cumulative ends of the first three segments
-    int ch[NCH], grp[NCH];
+    const int4* rec;              // sorted records of the bucket
+    const char* wts_lane[NCH];    // weights of (b, :, :, cam, l, group of this lane's chunk j), as bytes
+    const char* gout_lane[NCH];   // grad_out of batch element b at this lane's channels of chunk j, as bytes
+    unsigned c_bytes, w_stride_bytes;
+    int beg[4];                   // begin of the corner-1/2/3/4 segments in rec[]
+    int e1, e2, e3;               // cumulative ends of the first three segments
 };
+
+// per-lane channel ownership, fixed for the whole kernel
+template <int V, int NCH>
+struct LaneMap {
+    int ch[NCH], grp[NCH];
+    bool act[NCH];
+    __device__ __forceinline__ void init(int C, int G) {
+        const int lane = threadIdx.x & 31, gd = C / G;
+#pragma unroll
+        for (int j = 0; j < NCH; ++j) {
+            const int c_raw = (j * 32 + lane) * V;
+            act[j] = c_raw < C;
+            ch[j] = act[j] ? c_raw : C - V;    // clamped lanes compute values nobody stores
+            grp[j] = ch[j] / gd;
+        }
+    }
+};
+
+template <int V, int NCH>
+__device__ __forceinline__ void row_ctx_from_entry(RowCtx<V, NCH>& cx, const LaneMap<V, NCH>& lm, const GfeatParams& p,
+                                                   int b_idx, int packed) {
+    const Dims& d = p.d;
+    const int cam = packed & 0xff, l = (packed >> 8) & 0xff, rcl = packed >> 16;
+    const size_t AP = (size_t)d.A * d.P;
+    cx.rec = p.rec + ((size_t)b_idx * d.cams * d.L + rcl) * AP;
+    const float* wts = p.weights + (((size_t)b_idx * AP * d.cams + cam) * d.L + l) * d.G;
+    const float* gout = p.grad_out + (size_t)b_idx * d.A * d.C;
+#pragma unroll
+    for (int j = 0; j < NCH; ++j) {
+        cx.wts_lane[j] = reinterpret_cast<const char*>(wts + lm.grp[j]);
+        cx.gout_lane[j] = reinterpret_cast<const char*>(gout + lm.ch[j]);
+    }
+}
 
 // accumulate contributions [c_lo, c_hi) of one row, indices in the row's concatenated
 // (corner1, corner2, corner3, corner4) order -- the fixed summation order of this library.
+// Contributions are consumed in batches whose loads are all issued before the first FMA; a short last
+// batch is padded with copies of the range's last contribution at coefficient 0, so a typical row (a
+// handful of contributions) costs one memory round trip instead of one per contribution.  Addresses are
+// one 64-bit base per tensor plus 32-bit byte offsets (the loop is issue-bound otherwise).
 template <int V, int NCH>
 __device__ __forceinline__ void accumulate_row(const RowCtx<V, NCH>& cx, int c_lo, int c_hi, float (&acc)[NCH][V]) {
+    // contributions whose loads are in flight together: 64 data registers per lane
+    constexpr int kRegsPer = NCH * (V + 1);
+    constexpr int kReduceBatch = (kRegsPer <= 10) ? 8 : (kRegsPer <= 20) ? 4 : (kRegsPer <= 40) ? 2 : 1;
+    constexpr bool kConstChunks = (V > 1);   // vector path: chunk j sits j*32*V channels after chunk 0
     const int lane = threadIdx.x & 31;
     for (int v0 = c_lo; v0 < c_hi; v0 += 32) {
-        // lane-parallel metadata for up to 32 contributions
-        const int v = v0 + lane;
-        int go_off = 0, w_off = 0;
-        float coef = 0.f;
-        if (v < c_hi) {
-            const int k = (v >= cx.e1) + (v >= cx.e2) + (v >= cx.e3);
-            const int first = (k == 0) ? 0 : (k == 1) ? cx.e1 : (k == 2) ? cx.e2 : cx.e3;
-            const int bk = (k == 0) ? cx.beg[0] : (k == 1) ? cx.beg[1] : (k == 2) ? cx.beg[2] : cx.beg[3];
-            const int s_id = __ldg(cx.rec + bk + (v - first));
-            const float2 xy = __ldg(cx.loc2 + (size_t)s_id * cx.cams);
-            const Quad q = quad_setup(xy.x, xy.y, cx.h, cx.w);
-            coef = (k == 0) ? q.hh * q.hw : (k == 1) ? q.hh * q.lw : (k == 2) ? q.lh * q.hw : q.lh * q.lw;
-            go_off = (s_id / cx.P) * cx.C;
-            w_off = s_id * cx.w_stride;     // < 2^31 checked on the host
-        }
+        // lane-parallel metadata for up to 32 contributions (lanes past the end clamp onto the last one)
+        const int v = min(v0 + lane, c_hi - 1);
+        const int k = (v >= cx.e1) + (v >= cx.e2) + (v >= cx.e3);
+        const int first = (k == 0) ? 0 : (k == 1) ? cx.e1 : (k == 2) ? cx.e2 : cx.e3;
+        const int bk = (k == 0) ? cx.beg[0] : (k == 1) ? cx.beg[1] : (k == 2) ? cx.beg[2] : cx.beg[3];
+        const int4 e = __ldg(cx.rec + bk + (v - first));
+        const float lh = __int_as_float(e.z), lw = __int_as_float(e.w);
+        const float hh = 1.f - lh, hw = 1.f - lw;    // same expressions as quad_setup()
+        float coef = (k == 0) ? hh * hw : (k == 1) ? hh * lw : (k == 2) ? lh * hw : lh * lw;
+        if (v0 + lane >= c_hi) coef = 0.f;
+        const unsigned go_off = (unsigned)e.y * cx.c_bytes;           // < 2^32 checked on the host
+        const unsigned w_off = (unsigned)e.x * cx.w_stride_bytes;
         const int cnt = min(32, c_hi - v0);
-#pragma unroll 4
-        for (int m = 0; m < cnt; ++m) {
-            const int go_m = __shfl_sync(0xffffffffu, go_off, m);
-            const int w_m = __shfl_sync(0xffffffffu, w_off, m);
-            const float cf = __shfl_sync(0xffffffffu, coef, m);
+        for (int m0 = 0; m0 < cnt; m0 += kReduceBatch) {
+            float g[kReduceBatch][NCH][V];
+            float wg[kReduceBatch][NCH];
 #pragma unroll
-            for (int j = 0; j < NCH; ++j) {
-                float g[V];
-                VecIO<float, V>::load(cx.gout + go_m + cx.ch[j], g);
-                const float wg = __ldg(cx.wts + w_m + cx.grp[j]) * cf;
+            for (int u = 0; u < kReduceBatch; ++u) {
+                const int m = min(m0 + u, 31);
+                const unsigned go_m = __shfl_sync(0xffffffffu, go_off, m);
+                const unsigned w_m = __shfl_sync(0xffffffffu, w_off, m);
+                const float cf = __shfl_sync(0xffffffffu, coef, m);
+                const char* g0 = cx.gout_lane[0] + go_m;
 #pragma unroll
-                for (int e = 0; e < V; ++e) acc[j][e] = __fmaf_rn(wg, g[e], acc[j][e]);
+                for (int j = 0; j < NCH; ++j) {
+                    const char* gp = kConstChunks ? g0 + j * 32 * V * 4 : cx.gout_lane[j] + go_m;
+                    VecIO<float, V>::load(reinterpret_cast<const float*>(gp), g[u][j]);
+                    wg[u][j] = __ldg(reinterpret_cast<const float*>(cx.wts_lane[j] + w_m)) * cf;
+                }
             }
+#pragma unroll
+            for (int u = 0; u < kReduceBatch; ++u)
+#pragma unroll
+                for (int j = 0; j < NCH; ++j) {
+                    if constexpr (V % 2 == 0) {
+#pragma unroll
+                        for (int q = 0; q < V; q += 2) {
+                            const float2 r = __ffma2_rn(make_float2(wg[u][j], wg[u][j]),
+                                                        make_float2(g[u][j][q], g[u][j][q + 1]),
+                                                        make_float2(acc[j][q], acc[j][q + 1]));
+                            acc[j][q] = r.x;
+                            acc[j][q + 1] = r.y;
+                        }
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < V; ++q) acc[j][q] = __fmaf_rn(wg[u][j], g[u][j][q], acc[j][q]);
+                    }
+                }
         }
     }
 }
 
-// row (y,x) of a (cam,level) of size h x w: the four quad-key segments that contribute to it
-__device__ __forceinline__ int row_segments(const int* __restrict__ seg, int row, int w, int (&beg)[4], int& e1, int& e2,
-                                            int& e3) {
-    const int y = row / w, x = row - y * w;
-    const int k4 = y * (w + 1) + x;            // quad (y-1,x-1): this row is its corner 4
-    const int k1 = k4 + (w + 1) + 1;           // quad (y,x):     corner 1
-    const int sc = __ldg(seg + k1 - 1), sa = __ldg(seg + k1), sb = __ldg(seg + k1 + 1);
-    const int sd = __ldg(seg + k4), se = __ldg(seg + k4 + 1), sf = __ldg(seg + k4 + 2);
+// row (y,x) of a bucket: the four quad-key segments that contribute to it
+__device__ __forceinline__ int row_segments(const int* __restrict__ seg_bucket, const Bands& g, int y, int x,
+                                            int (&beg)[4], int& e1, int& e2, int& e3) {
+    // quad (y-1,x-1) -> padded (y, x): this row is its corner 4; quad (y,x) -> padded (y+1, x+1): corner 1
+    const int j4 = y / g.RB, j1 = (y + 1) / g.RB;
+    const int* t4 = seg_bucket + (size_t)j4 * g.tab + (y - j4 * g.RB) * g.row_keys + x;
+    const int* t1 = seg_bucket + (size_t)j1 * g.tab + (y + 1 - j1 * g.RB) * g.row_keys + x + 1;
+    const int sc = __ldg(t1 - 1), sa = __ldg(t1), sb = __ldg(t1 + 1);
+    const int sd = __ldg(t4), se = __ldg(t4 + 1), sf = __ldg(t4 + 2);
     // accumulation order: corner 1 [sa,sb), corner 2 [sc,sa), corner 3 [se,sf), corner 4 [sd,se)
     beg[0] = sa; beg[1] = sc; beg[2] = se; beg[3] = sd;
     e1 = sb - sa;
@@ -369,190 +579,192 @@ __device__ __forceinline__ int row_segments(const int* __restrict__ seg, int row
     return e3 + (se - sd);
 }
 
-template <typename T, int V, int NCH>
-__global__ void __launch_bounds__(kReduceWarps * 32) dfa_gfeat_reduce_kernel(const GfeatParams p) {
-    constexpr int kRowsPerWarp = kRowsPerTile / kReduceWarps;
+// grid (ceil(num_feat / kClassifyThreads), bs), block kClassifyThreads
+__global__ void __launch_bounds__(kClassifyThreads) dfa_row_classify_kernel(const GfeatParams p) {
     const Dims d = p.d;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31;
     const int b_idx = blockIdx.y;
     const int n_cl = d.cams * d.L;
-    const int AP = d.A * d.P;
-    const int gd = d.C / d.G;
-
-    __shared__ int s_tile[8];                  // cl, row0, h, w, start, segoff
-    __shared__ int s_beg[kRowsPerTile][4];
-    __shared__ int s_end[kRowsPerTile][4];     // e1, e2, e3, n
-
-    if (warp == 0) {
-        // tile decode, lane-parallel over the (level, cam) list ordered coarsest level first
-        int t = blockIdx.x, found = -1, row0 = 0, segoff = 0;
-        for (int base = 0; base < n_cl && found < 0; base += 32) {
-            const int i = base + lane;
-            int cl_i = -1, nt = 0;
-            if (i < n_cl) {
-                const int l = d.L - 1 - i / d.cams, cam = i - (i / d.cams) * d.cams;
-                cl_i = cam * d.L + l;
-                nt = (__ldg(p.shapes + cl_i * 2) * __ldg(p.shapes + cl_i * 2 + 1) + kRowsPerTile - 1) / kRowsPerTile;
-            }
-            int inc = nt;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int u = __shfl_up_sync(0xffffffffu, inc, o);
-                if (lane >= o) inc += u;
-            }
-            const unsigned hit = __ballot_sync(0xffffffffu, i < n_cl && t < inc);
-            if (hit) {
-                const int src = __ffs(hit) - 1;
-                found = __shfl_sync(0xffffffffu, cl_i, src);
-                row0 = (t - (__shfl_sync(0xffffffffu, inc, src) - __shfl_sync(0xffffffffu, nt, src))) * kRowsPerTile;
-            } else {
-                t -= __shfl_sync(0xffffffffu, inc, 31);
-            }
-        }
-        if (found >= 0) {
-            for (int i = lane; i < found; i += 32)
-                segoff += (__ldg(p.shapes + i * 2) + 1) * (__ldg(p.shapes + i * 2 + 1) + 1) + 1;
-            segoff = __reduce_add_sync(0xffffffffu, segoff);
-        }
-        if (lane == 0) {
-            s_tile[0] = found;
-            s_tile[1] = row0;
-            if (found >= 0) {
-                s_tile[2] = __ldg(p.shapes + found * 2);
-                s_tile[3] = __ldg(p.shapes + found * 2 + 1);
-                s_tile[4] = __ldg(p.starts + found);
-                s_tile[5] = segoff;
-            }
-        }
-    }
-    __syncthreads();
-    const int cl = s_tile[0];
-    if (cl < 0) return;
-    const int row0 = s_tile[1], h = s_tile[2], w = s_tile[3], start = s_tile[4];
-    const int cam = cl / d.L, l = cl - cam * d.L;
-    const int* seg = p.seg + (size_t)b_idx * p.seg_stride + s_tile[5];
-    T* gfeat = reinterpret_cast<T*>(p.g_feat) + ((size_t)b_idx * d.num_feat + start) * d.C;
-
-    // segment bounds of every row of the tile, one thread per row
-    if (tid < kRowsPerTile) {
-        const int row = row0 + tid;
-        int beg[4], e1 = 0, e2 = 0, e3 = 0, n = -1;
-        beg[0] = beg[1] = beg[2] = beg[3] = 0;
-        if (row < h * w) {
-            n = row_segments(seg, row, w, beg, e1, e2, e3);
-            if (n > kHeavyRow) {
-                const int slot = atomicAdd(p.heavy_count, 1);
-                p.heavy_list[slot] = make_int2(b_idx * n_cl + cl, row);
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < 4; ++k) s_beg[tid][k] = beg[k];
-        s_end[tid][0] = e1; s_end[tid][1] = e2; s_end[tid][2] = e3; s_end[tid][3] = n;
-    }
+    __shared__ int s_tab[kMaxCamLevels * 3];
+    load_level_table(s_tab, p.shapes, p.starts, n_cl);
     __syncthreads();
 
+    const int row = blockIdx.x * kClassifyThreads + tid;
+    int n = 0, cl = -1;
+    int beg[4] = {0, 0, 0, 0}, e1 = 0, e2 = 0, e3 = 0;
+    if (row < d.num_feat) {
+        for (int i = 0; i < n_cl; ++i) {
+            const int st = s_tab[i * 3 + 2];
+            if (row >= st && row < st + s_tab[i * 3] * s_tab[i * 3 + 1]) cl = i;
+        }
+        if (cl >= 0) {
+            const int h = s_tab[cl * 3], w = s_tab[cl * 3 + 1], st = s_tab[cl * 3 + 2];
+            const Bands g = band_geometry(h, w, p.NB);
+            const int r = row - st, y = r / w, x = r - y * w;
+            n = row_segments(p.seg + (size_t)b_idx * p.seg_stride + seg_offset(st), g, y, x, beg, e1, e2, e3);
+        }
+    }
+    const bool heavy = n > kHeavyRow, light = n > 0 && !heavy;
+    const int cam = (cl >= 0) ? cl / d.L : 0;
+    const int4 q0 = make_int4(b_idx * d.num_feat + row, n, b_idx, cam | ((cl - cam * d.L) << 8) | (cl << 16));
+    const int4 q1 = make_int4(beg[0], beg[1], beg[2], beg[3]);
+    const int4 q2 = make_int4(e1, e2, e3, 0);
+    // light rows: warp-aggregated append, one integer atomic per warp
+    const unsigned bl = __ballot_sync(0xffffffffu, light);
+    int base_l = 0;
+    if (lane == 0 && bl) base_l = atomicAdd(p.counters + 1, __popc(bl));
+    base_l = __shfl_sync(0xffffffffu, base_l, 0);
+    if (light) {
+        int4* e = p.light_list + (size_t)(base_l + __popc(bl & ((1u << lane) - 1u))) * (kEntryInts / 4);
+        e[0] = q0; e[1] = q1; e[2] = q2;
+    }
+    // heavy rows: one entry per unit of kHeavyUnit contributions; multi-unit rows get partial-sum slots
+    if (heavy) {
+        const int units = (n + kHeavyUnit - 1) / kHeavyUnit;
+        const int at = atomicAdd(p.counters + 0, units);
+        int slot = -1;
+        if (units > 1) {
+            slot = atomicAdd(p.counters + 2, units);
+            p.unit_done[slot] = 0;
+        }
+        for (int u = 0; u < units; ++u) {
+            int4* e = p.heavy_list + (size_t)(at + u) * (kEntryInts / 4);
+            e[0] = q0; e[1] = q1; e[2] = q2;
+            e[3] = make_int4(u | (units << 16), slot, 0, 0);
+        }
+    }
+}
+
+// grid (kLightCtas), block kLightWarps*32: persistent warps, one light row at a time
+template <typename T, int V, int NCH>
+__global__ void __launch_bounds__(kLightWarps * 32, 2) dfa_gfeat_light_kernel(const GfeatParams p) {
+    const Dims d = p.d;
+    const int lane = threadIdx.x & 31;
+    const int n_light = p.counters[1];
+    const int gwarp = blockIdx.x * kLightWarps + (threadIdx.x >> 5), n_warps = gridDim.x * kLightWarps;
+
+    LaneMap<V, NCH> lm;
+    lm.init(d.C, d.G);
     RowCtx<V, NCH> cx;
-    cx.rec = p.rec + ((size_t)b_idx * n_cl + cl) * AP;
-    cx.loc2 = reinterpret_cast<const float2*>(p.loc) + (size_t)b_idx * AP * d.cams + cam;
-    cx.wts = p.weights + ((size_t)b_idx * AP * d.cams + cam) * d.L * d.G + (size_t)l * d.G;
-    cx.gout = p.grad_out + (size_t)b_idx * d.A * d.C;
-    cx.h = h; cx.w = w; cx.cams = d.cams; cx.P = d.P; cx.C = d.C; cx.w_stride = d.cams * d.L * d.G;
-    bool act[NCH];
-#pragma unroll
-    for (int j = 0; j < NCH; ++j) {
-        const int c_raw = (j * 32 + lane) * V;
-        act[j] = c_raw < d.C;
-        cx.ch[j] = act[j] ? c_raw : d.C - V;    // clamped lanes compute values nobody stores
-        cx.grp[j] = cx.ch[j] / gd;
-    }
-
+    cx.c_bytes = (unsigned)d.C * 4u;
+    cx.w_stride_bytes = (unsigned)(d.cams * d.L * d.G) * 4u;
+    const int* list = reinterpret_cast<const int*>(p.light_list);
+    int field = (gwarp < n_light && lane < 12) ? __ldg(list + (size_t)gwarp * kEntryInts + lane) : 0;
 #pragma unroll 1
-    for (int rr = 0; rr < kRowsPerWarp; ++rr) {
-        const int r = rr * kReduceWarps + warp;
-        const int n = s_end[r][3];
-        if (n < 0 || n > kHeavyRow) continue;     // beyond the level / handled by the heavy kernel
+    for (int i = gwarp; i < n_light; i += n_warps) {
+        const int cur = field;
+        if (i + n_warps < n_light && lane < 12) field = __ldg(list + (size_t)(i + n_warps) * kEntryInts + lane);   // prefetch
+        const int grow = __shfl_sync(0xffffffffu, cur, 0);
+        const int rn = __shfl_sync(0xffffffffu, cur, 1);
+        row_ctx_from_entry<V, NCH>(cx, lm, p, __shfl_sync(0xffffffffu, cur, 2), __shfl_sync(0xffffffffu, cur, 3));
+#pragma unroll
+        for (int k = 0; k < 4; ++k) cx.beg[k] = __shfl_sync(0xffffffffu, cur, 4 + k);
+        cx.e1 = __shfl_sync(0xffffffffu, cur, 8);
+        cx.e2 = __shfl_sync(0xffffffffu, cur, 9);
+        cx.e3 = __shfl_sync(0xffffffffu, cur, 10);
         float acc[NCH][V];
 #pragma unroll
         for (int j = 0; j < NCH; ++j)
 #pragma unroll
             for (int e = 0; e < V; ++e) acc[j][e] = 0.f;
-        if (n > 0) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) cx.beg[k] = s_beg[r][k];
-            cx.e1 = s_end[r][0]; cx.e2 = s_end[r][1]; cx.e3 = s_end[r][2];
-            accumulate_row<V, NCH>(cx, 0, n, acc);
-        }
+        accumulate_row<V, NCH>(cx, 0, rn, acc);
+        T* dst = reinterpret_cast<T*>(p.g_feat) + (size_t)grow * d.C;
 #pragma unroll
         for (int j = 0; j < NCH; ++j)
-            if (act[j]) VecIO<T, V>::store(gfeat + (size_t)(row0 + r) * d.C + cx.ch[j], acc[j]);
+            if (lm.act[j]) VecIO<T, V>::store(dst + lm.ch[j], acc[j]);
     }
 }
 
-// grid (kHeavyCtas), block kReduceWarps*32: persistent walk over the heavy-row list
+// grid (kHeavyCtas), block kHeavyWarps*32: persistent CTAs stride over the heavy UNITS.  A unit is up to
+// kHeavyUnit consecutive contributions of one row, split evenly over the 8 warps; warp 0 adds the 8
+// partials in warp order.  Single-unit rows are written directly; units of a longer row go to
+// partial-sum slots and the CTA that finishes last adds them in unit order (which CTA that is does not
+// influence the result).
 template <typename T, int V, int NCH>
-__global__ void __launch_bounds__(kReduceWarps * 32) dfa_gfeat_heavy_kernel(const GfeatParams p) {
+__global__ void __launch_bounds__(kHeavyWarps * 32, 2) dfa_gfeat_heavy_kernel(const GfeatParams p) {
     constexpr int CPAD = NCH * 32 * V;
     const Dims d = p.d;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int n_cl = d.cams * d.L;
-    const int AP = d.A * d.P;
-    const int gd = d.C / d.G;
-    __shared__ __align__(16) float red[kReduceWarps * CPAD];
+    __shared__ __align__(16) float red[kHeavyWarps * CPAD];
+    __shared__ int s_ent[kEntryInts];
 
-    const int n_heavy = *p.heavy_count;
+    const int n_units = p.counters[0];
+    LaneMap<V, NCH> lm;
+    lm.init(d.C, d.G);
     RowCtx<V, NCH> cx;
-    bool act[NCH];
+    cx.c_bytes = (unsigned)d.C * 4u;
+    cx.w_stride_bytes = (unsigned)(d.cams * d.L * d.G) * 4u;
+
+    for (int i = blockIdx.x; i < n_units; i += gridDim.x) {
+        if (tid < kEntryInts) s_ent[tid] = reinterpret_cast<const int*>(p.heavy_list)[(size_t)i * kEntryInts + tid];
+        __syncthreads();
+        const int grow = s_ent[0], n = s_ent[1];
+        const int u = s_ent[12] & 0xffff, units = s_ent[12] >> 16, slot = s_ent[13];
+        row_ctx_from_entry<V, NCH>(cx, lm, p, s_ent[2], s_ent[3]);
 #pragma unroll
-    for (int j = 0; j < NCH; ++j) {
-        const int c_raw = (j * 32 + lane) * V;
-        act[j] = c_raw < d.C;
-        cx.ch[j] = act[j] ? c_raw : d.C - V;
-        cx.grp[j] = cx.ch[j] / gd;
-    }
-    cx.cams = d.cams; cx.P = d.P; cx.C = d.C; cx.w_stride = d.cams * d.L * d.G;
+        for (int k = 0; k < 4; ++k) cx.beg[k] = s_ent[4 + k];
+        cx.e1 = s_ent[8]; cx.e2 = s_ent[9]; cx.e3 = s_ent[10];
 
-    for (int e = blockIdx.x; e < n_heavy; e += gridDim.x) {
-        const int2 ent = p.heavy_list[e];
-        const int b_idx = ent.x / n_cl, cl = ent.x - b_idx * n_cl, row = ent.y;
-        const int cam = cl / d.L, l = cl - cam * d.L;
-        const int h = __ldg(p.shapes + cl * 2), w = __ldg(p.shapes + cl * 2 + 1), start = __ldg(p.starts + cl);
-        int segoff = 0;
-        for (int i = 0; i < cl; ++i) segoff += (__ldg(p.shapes + i * 2) + 1) * (__ldg(p.shapes + i * 2 + 1) + 1) + 1;
-        const int* seg = p.seg + (size_t)b_idx * p.seg_stride + segoff;
-        const int n = row_segments(seg, row, w, cx.beg, cx.e1, cx.e2, cx.e3);
-        cx.rec = p.rec + ((size_t)b_idx * n_cl + cl) * AP;
-        cx.loc2 = reinterpret_cast<const float2*>(p.loc) + (size_t)b_idx * AP * d.cams + cam;
-        cx.wts = p.weights + ((size_t)b_idx * AP * d.cams + cam) * d.L * d.G + (size_t)l * d.G;
-        cx.gout = p.grad_out + (size_t)b_idx * d.A * d.C;
-        cx.h = h; cx.w = w;
-
-        // contiguous ranges in multiples of 32 so every warp runs full metadata batches
-        int per = (n + kReduceWarps - 1) / kReduceWarps;
-        per = (per + 31) & ~31;
+        const int u_lo = u * kHeavyUnit, u_hi = min(n, u_lo + kHeavyUnit);
+        int per = (u_hi - u_lo + kHeavyWarps - 1) / kHeavyWarps;
+        per = (per + 7) & ~7;                      // whole load batches per warp
+        const int c_lo = min(u_hi, u_lo + warp * per), c_hi = min(u_hi, c_lo + per);
         float acc[NCH][V];
 #pragma unroll
         for (int j = 0; j < NCH; ++j)
 #pragma unroll
             for (int q = 0; q < V; ++q) acc[j][q] = 0.f;
-        accumulate_row<V, NCH>(cx, min(n, warp * per), min(n, (warp + 1) * per), acc);
+        if (c_lo < c_hi) accumulate_row<V, NCH>(cx, c_lo, c_hi, acc);
 #pragma unroll
         for (int j = 0; j < NCH; ++j)
 #pragma unroll
             for (int q = 0; q < V; ++q) red[warp * CPAD + (j * 32 + lane) * V + q] = acc[j][q];
         __syncthreads();
         if (warp == 0) {
-            T* dst = reinterpret_cast<T*>(p.g_feat) + ((size_t)b_idx * d.num_feat + start + row) * d.C;
+            float sum[NCH][V];
 #pragma unroll
-            for (int j = 0; j < NCH; ++j) {
-                float sum[V];
+            for (int j = 0; j < NCH; ++j)
 #pragma unroll
                 for (int q = 0; q < V; ++q) {
                     float s = 0.f;
 #pragma unroll
-                    for (int ww = 0; ww < kReduceWarps; ++ww) s += red[ww * CPAD + (j * 32 + lane) * V + q];
-                    sum[q] = s;
+                    for (int ww = 0; ww < kHeavyWarps; ++ww) s += red[ww * CPAD + (j * 32 + lane) * V + q];
+                    sum[j][q] = s;
                 }
-                if (act[j]) VecIO<T, V>::store(dst + cx.ch[j], sum);
+            bool write_row = units == 1;
+            if (units > 1) {
+                float* mine = p.partial + (size_t)(slot + u) * d.C;
+#pragma unroll
+                for (int j = 0; j < NCH; ++j)
+                    if (lm.act[j]) VecIO<float, V>::store(mine + lm.ch[j], sum[j]);
+                __threadfence();
+                __syncwarp();
+                int old = 0;
+                if (lane == 0) old = atomicAdd(p.unit_done + slot, 1);
+                old = __shfl_sync(0xffffffffu, old, 0);
+                if (old == units - 1) {        // every unit of this row is in memory: add them in unit order
+                    __threadfence();
+                    write_row = true;
+#pragma unroll
+                    for (int j = 0; j < NCH; ++j)
+#pragma unroll
+                        for (int q = 0; q < V; ++q) sum[j][q] = 0.f;
+                    for (int uu = 0; uu < units; ++uu) {
+                        const float* part = p.partial + (size_t)(slot + uu) * d.C;
+#pragma unroll
+                        for (int j = 0; j < NCH; ++j) {
+                            if (!lm.act[j]) continue;
+#pragma unroll
+                            for (int q = 0; q < V; ++q) sum[j][q] += __ldcg(part + lm.ch[j] + q);
+                        }
+                    }
+                }
+            }
+            if (write_row) {
+                T* dst = reinterpret_cast<T*>(p.g_feat) + (size_t)grow * d.C;
+#pragma unroll
+                for (int j = 0; j < NCH; ++j)
+                    if (lm.act[j]) VecIO<T, V>::store(dst + lm.ch[j], sum[j]);
             }
         }
         __syncthreads();

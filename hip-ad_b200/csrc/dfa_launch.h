@@ -19,7 +19,9 @@ struct KernelShape {
 
 // picks the kernel family member for (C, G, alignment); ok=false -> HIPAD_DFA_ERR_UNSUPPORTED
 KernelShape pick_shape(ElemType t, int C, int G, bool aligned16);
-int choose_slices(long long rows, int pairs, int target_ctas);
+// point slices per output row: enough CTAs to fill the machine, and few enough pairs per slice that the
+// slice's gather metadata (bytes_per_pair each) fits the shared-memory budget; 0 if max_slices cannot do it
+int choose_slices(long long rows, int pairs, int target_ctas, int bytes_per_pair, int max_slices);
 
 struct FwdArgs {
     ElemType type;
@@ -54,7 +56,8 @@ struct BwdArgs {
     void* workspace;
     size_t workspace_bytes;
     cudaStream_t stream;
-    int stage_mask;   // bit0 sample-major (g_w,g_loc), bit1 bucket sort, bit2 feature-major reduce
+    int stage_mask;   // bit0 sample-major (g_w,g_loc) + zero fill of g_feat, bit1 compaction + band sort, bit2 reduce
+    bool separate_zero_fill;   // measurement: never fold the zero fill into the sample-major kernel
 };
 int launch_backward(const BwdArgs& a);
 size_t backward_workspace_bytes(const Dims& d);

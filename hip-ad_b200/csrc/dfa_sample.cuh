@@ -44,6 +44,8 @@ struct SampleParams {
     const float* proj;        // kFused [bs,cams,4,4]
     const float* image_wh;    // kFused [bs,cams,2] or null
     float* loc_out;           // kFused optional [bs,A,P,cams,2]
+    uint4* zero_ptr;          // kBwd optional: dense buffer (grad_mc_ms_feat) this launch zero-fills on the side
+    long long zero_n16;       //               its size in 16-byte units
     Dims d;
     int S;    // CTAs per output row
     int PS;   // (p,cam) pairs per slice = ceil(P*cams / S)
@@ -133,6 +135,15 @@ __global__ void __launch_bounds__(kWarps * 32) dfa_sample_kernel(const SamplePar
     float* s_stat = reinterpret_cast<float*>(smem_raw + so.stat);    // kFused: m[G], inv_s[G], scratch 2*G
     float* s_red2 = reinterpret_cast<float*>(smem_raw + so.red2);    // kFused: per-thread (m,s)
 
+    if (kMode == kBwd && p.zero_n16 > 0) {
+        // Dense zero fill of the feature gradient, 1/gridDim of it per CTA.  The stores are fire-and-forget:
+        // they drain to HBM while this CTA waits on its gather loads (the write path is otherwise idle here).
+        const long long per = (p.zero_n16 + gridDim.x - 1) / gridDim.x;
+        const long long z0 = (long long)blockIdx.x * per;
+        const long long z1 = (z0 + per < p.zero_n16) ? z0 + per : p.zero_n16;
+        const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+        for (long long i = z0 + tid; i < z1; i += kThreads) p.zero_ptr[i] = z;
+    }
     load_level_table(tab, p.shapes, p.starts, n_cl);
     if (kMode == kFused) {
         for (int i = tid; i < d.cams * 12; i += kThreads)

@@ -70,16 +70,16 @@ int hipad_dfa_forward_bf16(float *output, const uint16_t *mc_ms_feat,
                            void *stream);
 
 /* ---- backward: replaces deformable_aggregation_grad() (deformable_aggregation_cuda.cu:291-318) ----
- * Bytes of scratch the backward needs (sorted sample records + segment table).  Pure host
- * arithmetic on the sizes; the result is an upper bound valid for any spatial_shape whose
- * rows sum to num_feat. */
+ * Bytes of scratch the backward needs (compacted visible samples, sorted records, segment
+ * tables).  Pure host arithmetic on the sizes; valid for any spatial_shape / scale_start_index
+ * whose (cam, level) row ranges are disjoint and lie inside [0, num_feat). */
 size_t hipad_dfa_backward_workspace_bytes(int batch_size, int num_cams, int num_feat,
                                           int num_embeds, int num_scale, int num_anchors,
                                           int num_pts, int num_groups);
 
 /* Writes ALL of grad_mc_ms_feat [bs,num_feat,C], grad_sampling_location and grad_weights
  * (zeros where nothing contributes).  grad_mc_ms_feat may be NULL: the feature-gradient pass is
- * then skipped (frozen backbone).  workspace: device memory, 256-byte aligned, at least
+ * then skipped (frozen backbone) and workspace may be NULL.  workspace: device memory, 256-byte aligned, at least
  * hipad_dfa_backward_workspace_bytes(...) bytes, private to this call until it completes. */
 int hipad_dfa_backward_f32(const float *mc_ms_feat,
                            const int32_t *spatial_shape, const int32_t *scale_start_index,
@@ -101,10 +101,12 @@ int hipad_dfa_backward_bf16(const uint16_t *mc_ms_feat,
                             void *workspace, size_t workspace_bytes, void *stream);
 
 /* Measurement variant of the backward: runs only the kernels selected by stage_mask
- * (bit0 = sample-major kernel writing grad_weights/grad_sampling_location, bit1 = per-(b,cam,level)
- * bucket sort into the workspace, bit2 = feature-major reduce writing grad_mc_ms_feat; 7 = the full
- * backward).  bench.py uses it to put CUDA events around each kernel; results are only meaningful
- * when the stages are issued in order on one stream with the same workspace. */
+ * (bit0 = sample-major kernel writing grad_weights/grad_sampling_location, which also zero-fills
+ * grad_mc_ms_feat; bit1 = visible-sample compaction + per-(b,cam,level,band) sort into the workspace;
+ * bit2 = feature-major reduce overwriting the touched rows of grad_mc_ms_feat; 7 = the full backward;
+ * bit3 = keep the zero fill in its own kernel instead of folding it into the sample-major kernel).
+ * bench.py uses it to put CUDA events around each stage; results are only meaningful when the stages
+ * are issued in order on one stream with the same workspace. */
 int hipad_dfa_backward_stages(int feat_is_bf16, int stage_mask,
                               const void *mc_ms_feat,
                               const int32_t *spatial_shape, const int32_t *scale_start_index,

@@ -52,5 +52,5 @@ for r in range(reps):
     ev.append(e)
 torch.cuda.synchronize()
 for e in ev[1:]:
-    print(kind, "bs", bs, "us: fwd %.1f  bwd_sample %.1f  sort %.1f  reduce %.1f" %
+    print(kind, "bs", bs, "us: fwd %.1f  bwd_sample+zero %.1f  compact+sort %.1f  rows+heavy %.1f" %
           tuple(e[i].elapsed_time(e[i + 1]) * 1e3 for i in range(4)))

@@ -1,0 +1,12 @@
+#!/bin/bash
+# bench.py runs + launch list.  usage: bash scripts/gpu_bench.sh <tag>
+set -u
+TAG=${1:-bench}
+OUT=gpurun_out/$TAG
+mkdir -p $OUT
+timeout 600 python bench.py > $OUT/bench_f32.json 2> $OUT/bench_f32.err; echo "bench rc=$?" | tee -a $OUT/status.txt
+timeout 600 python bench.py --dtype bf16 --skip-cpu > $OUT/bench_bf16.json 2> $OUT/bench_bf16.err; echo "bench bf16 rc=$?" | tee -a $OUT/status.txt
+timeout 600 python bench.py --bs 4 --skip-cpu --steps 10 > $OUT/bench_f32_bs4.json 2> $OUT/bench_f32_bs4.err; echo "bench bs4 rc=$?" | tee -a $OUT/status.txt
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $OUT/launches.csv \
+    python bench.py --steps 2 --warmup 3 --skip-e2e --skip-cpu --no-graph > $OUT/ncu_launches.log 2>&1; echo "ncu list rc=$?" | tee -a $OUT/status.txt
+cat $OUT/bench_f32.json; tail -5 $OUT/bench_f32_bs4.err
