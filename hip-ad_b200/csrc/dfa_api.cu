@@ -56,6 +56,7 @@ int backward_common(ElemType t, const void* feat, const int32_t* shapes, const i
     a.stream = reinterpret_cast<cudaStream_t>(stream);
     a.stage_mask = stage_mask & 7;
     a.separate_zero_fill = (stage_mask & 8) != 0;
+    a.classify_only = (stage_mask & 16) != 0;
     return launch_backward(a);
 }
 }  // namespace
@@ -87,6 +88,11 @@ int hipad_dfa_forward_bf16(float* output, const uint16_t* mc_ms_feat, const int3
                            int num_pts, int num_groups, void* stream) {
     return forward_common(kBF16, output, mc_ms_feat, spatial_shape, scale_start_index, sample_location, weights,
                           batch_size, num_cams, num_feat, num_embeds, num_scale, num_anchors, num_pts, num_groups, stream);
+}
+
+size_t hipad_dfa_debug_counters_offset(int bs, int cams, int num_feat, int C, int L, int A, int P, int G) {
+    if (bad_dims(bs, cams, num_feat, C, L, A, P, G)) return 0;
+    return backward_counters_offset(mk(bs, cams, num_feat, C, L, A, P, G));
 }
 
 size_t hipad_dfa_backward_workspace_bytes(int batch_size, int num_cams, int num_feat, int num_embeds, int num_scale,
@@ -125,7 +131,7 @@ int hipad_dfa_backward_stages(int feat_is_bf16, int stage_mask, const void* mc_m
     return backward_common(feat_is_bf16 ? kBF16 : kF32, mc_ms_feat, spatial_shape, scale_start_index, sample_location,
                            weights, grad_output, grad_mc_ms_feat, grad_sampling_location, grad_weights, batch_size,
                            num_cams, num_feat, num_embeds, num_scale, num_anchors, num_pts, num_groups, workspace,
-                           workspace_bytes, stream, stage_mask & 15);
+                           workspace_bytes, stream, stage_mask & 31);
 }
 
 int hipad_dfa_sample_indices(int32_t* indices, const int32_t* spatial_shape, const int32_t* scale_start_index,

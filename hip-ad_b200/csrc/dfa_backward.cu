@@ -1,15 +1,24 @@
 // dfa_backward.cu — backward launchers: sample-major (g_w, g_loc) + feature-major (g_feat).
 #include "dfa_dispatch.cuh"
 #include "dfa_gfeat.cuh"
+#include <cstdio>
 
 namespace hipad {
 
 namespace {
+// HIPAD_DFA_DEBUG_SYNC=1: synchronise after every launch of the backward and name the kernel that failed
+inline int debug_sync(const char* what, cudaStream_t st) {
+    static const int on = hipad_env_int("HIPAD_DFA_DEBUG_SYNC", 0);
+    if (!on) return 0;
+    const cudaError_t e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) fprintf(stderr, "hipad_dfa: %s failed: %s\n", what, cudaGetErrorString(e));
+    return (int)e;
+}
 constexpr size_t kAlign = 256;
 inline size_t align_up(size_t v) { return (v + kAlign - 1) / kAlign * kAlign; }
 
 struct WorkspaceLayout {
-    size_t vis_id, vis_xy, vis_cnt, rec, seg, cursor, sortbuf, heavy_list, light_list, partial, unit_done, counters, total;
+    size_t vis_id, vis_xy, vis_cnt, rec, seg, cursor, sortbuf, part_list, tiny_list, partial, unit_done, counters, total;
     size_t partial_slots;
     int seg_stride, n_chunks;
 };
@@ -28,43 +37,51 @@ WorkspaceLayout workspace_layout(const Dims& d) {
     w.seg = off;     off += align_up((size_t)d.bs * w.seg_stride * sizeof(int));
     w.cursor = off;  off += align_up((size_t)d.bs * n_cl * sizeof(int));
     w.sortbuf = off; off += align_up((size_t)d.bs * n_cl * 2 * AP * sizeof(unsigned long long));
-    // multi-unit rows: sum of ceil(n/kHeavyUnit) over rows with n > kHeavyUnit <= 2 * (4 * bs*AP*cams*L) / kHeavyUnit
-    w.partial_slots = (size_t)d.bs * AP * n_cl * 8 / kHeavyUnit + 1;
-    w.heavy_list = off;  off += align_up(((size_t)d.bs * d.num_feat + w.partial_slots) * kEntryInts * sizeof(int));
-    w.light_list = off;  off += align_up((size_t)d.bs * d.num_feat * kEntryInts * sizeof(int));
+    // part sums of rows with more than kPart contributions.  Worst case (every sample visible and piled onto few
+    // rows) would need bs*AP*cams*L*8/kPart slots; 1/4 of that covers every realistic input, and a row that finds no
+    // free slots is summed by a single warp instead (dfa_row_classify_kernel).
+    w.partial_slots = (size_t)d.bs * (AP * n_cl / 16 + 1024);
+    w.part_list = off;   off += align_up(((size_t)d.bs * d.num_feat + w.partial_slots) * kEntryInts * sizeof(int));
+    w.tiny_list = off;   off += align_up((size_t)d.bs * d.num_feat * kEntryInts * sizeof(int));
     w.partial = off;     off += align_up(w.partial_slots * d.C * sizeof(float));
     w.unit_done = off;   off += align_up(w.partial_slots * sizeof(int));
-    w.counters = off;    off += align_up(4 * sizeof(int));
+    w.counters = off;    off += align_up(8 * sizeof(int));
     w.total = off;
     return w;
+}
+
+template <typename T, int V, int NCH>
+int launch_reduce_nq(const GfeatParams& gp, cudaStream_t st) {
+#define HIPAD_NQ(NQ_)                                                                          \
+    case NQ_:                                                                                  \
+        dfa_gfeat_reduce_kernel<T, V, NCH, NQ_><<<kReduceCtas, 256, 0, st>>>(gp);              \
+        break
+    switch (gp.tiny_ok ? gp.d.C / 32 : 0) {
+        HIPAD_NQ(0); HIPAD_NQ(1); HIPAD_NQ(2); HIPAD_NQ(4); HIPAD_NQ(8);
+        default: return -2;
+    }
+#undef HIPAD_NQ
+    return (int)cudaGetLastError();
 }
 
 template <typename T>
 int launch_reduce(const GfeatParams& gp, KernelShape ks, cudaStream_t st) {
     constexpr int VV = 16 / (int)sizeof(T);
-#define HIPAD_RED(V_, NCH_)                                                                \
-    do {                                                                                   \
-        dfa_gfeat_light_kernel<T, V_, NCH_><<<kLightCtas, kLightWarps * 32, 0, st>>>(gp);  \
-        cudaError_t e_ = cudaGetLastError();                                               \
-        if (e_ != cudaSuccess) return (int)e_;                                             \
-        dfa_gfeat_heavy_kernel<T, V_, NCH_><<<kHeavyCtas, kHeavyWarps * 32, 0, st>>>(gp);  \
-        return (int)cudaGetLastError();                                                    \
-    } while (0)
     if (ks.vector) {
-        if (ks.nch == 1) HIPAD_RED(VV, 1);
-        if (ks.nch == 2) HIPAD_RED(VV, 2);
-        if (ks.nch == 3) HIPAD_RED(VV, 3);
-        if (ks.nch == 4) HIPAD_RED(VV, 4);
+        if (ks.nch == 1) return launch_reduce_nq<T, VV, 1>(gp, st);
+        if (ks.nch == 2) return launch_reduce_nq<T, VV, 2>(gp, st);
+        if (ks.nch == 3) return launch_reduce_nq<T, VV, 3>(gp, st);
+        if (ks.nch == 4) return launch_reduce_nq<T, VV, 4>(gp, st);
     } else {
-        if (ks.nch == 2) HIPAD_RED(1, 2);
-        if (ks.nch == 8) HIPAD_RED(1, 8);
+        if (ks.nch == 2) return launch_reduce_nq<T, 1, 2>(gp, st);
+        if (ks.nch == 8) return launch_reduce_nq<T, 1, 8>(gp, st);
     }
-#undef HIPAD_RED
     return -2;
 }
 }  // namespace
 
 size_t backward_workspace_bytes(const Dims& d) { return workspace_layout(d).total; }
+size_t backward_counters_offset(const Dims& d) { return workspace_layout(d).counters; }
 
 int launch_backward(const BwdArgs& a) {
     const Dims& d = a.d;
@@ -96,7 +113,8 @@ int launch_backward(const BwdArgs& a) {
     p.PS = (NP + p.S - 1) / p.S;
     const long long grid = rows * p.S;
     if (grid > 0x7fffffffLL) return -2;
-    const size_t smem = sample_smem_for(kBwd, d, ks, a.type, p.PS);
+    const int warps = choose_sample_warps(grid, d.G);
+    const size_t smem = sample_smem_for(kBwd, d, ks, a.type, p.PS, warps);
     if (smem > kSampleSmemBudget) return -2;
     const size_t gfeat_bytes = (size_t)d.bs * d.num_feat * d.C * (a.type == kF32 ? 4 : 2);
     if (a.stage_mask & 1) {
@@ -116,9 +134,10 @@ int launch_backward(const BwdArgs& a) {
             }
         }
         const int rc = (a.type == kF32)
-                           ? dispatch_sample<float, kBwd, false>(p, ks, (int)grid, smem, a.stream)
-                           : dispatch_sample<__nv_bfloat16, kBwd, false>(p, ks, (int)grid, smem, a.stream);
+                           ? dispatch_sample<float, kBwd, false>(p, ks, warps, (int)grid, smem, a.stream)
+                           : dispatch_sample<__nv_bfloat16, kBwd, false>(p, ks, warps, (int)grid, smem, a.stream);
         if (rc != 0) return rc;
+        if (int e = debug_sync("sample-major backward kernel", a.stream)) return e;
     }
     if (a.g_feat == nullptr) return 0;   // caller does not need the feature-map gradient
 
@@ -134,10 +153,11 @@ int launch_backward(const BwdArgs& a) {
     gp.seg = reinterpret_cast<int*>(ws + wl.seg);
     gp.cursor = reinterpret_cast<int*>(ws + wl.cursor);
     gp.sortbuf = reinterpret_cast<unsigned long long*>(ws + wl.sortbuf);
-    gp.heavy_list = reinterpret_cast<int4*>(ws + wl.heavy_list);
+    gp.part_list = reinterpret_cast<int4*>(ws + wl.part_list);
     gp.partial = reinterpret_cast<float*>(ws + wl.partial);
     gp.unit_done = reinterpret_cast<int*>(ws + wl.unit_done);
-    gp.light_list = reinterpret_cast<int4*>(ws + wl.light_list);
+    gp.partial_cap = (int)wl.partial_slots;
+    gp.tiny_list = reinterpret_cast<int4*>(ws + wl.tiny_list);
     gp.counters = reinterpret_cast<int*>(ws + wl.counters);
     gp.d = d;
     gp.seg_stride = wl.seg_stride;
@@ -146,6 +166,8 @@ int launch_backward(const BwdArgs& a) {
     const int buckets = d.cams * d.L * d.bs;
     int nb = (2 * 148) / buckets;
     gp.NB = nb < 1 ? 1 : (nb > kMaxBands ? kMaxBands : nb);
+    gp.tiny_ok = (ks.vector && (d.C == 32 || d.C == 64 || d.C == 128 || d.C == 256) && (d.C / d.G) % 32 == 0 &&
+                  hipad_env_int("HIPAD_DFA_TINY", 1) != 0) ? 1 : 0;
     if (a.stage_mask & 2) {
         dfa_vis_compact_kernel<<<dim3((unsigned)wl.n_chunks, (unsigned)d.cams, (unsigned)d.bs), kVisThreads, 0,
                                  a.stream>>>(gp);
@@ -158,6 +180,7 @@ int launch_backward(const BwdArgs& a) {
                                a.stream>>>(gp);
         e = cudaGetLastError();
         if (e != cudaSuccess) return (int)e;
+        if (int e2 = debug_sync("compaction / band sort", a.stream)) return e2;
     }
     if (!(a.stage_mask & 4)) return 0;
 
@@ -166,7 +189,11 @@ int launch_backward(const BwdArgs& a) {
                               kClassifyThreads, 0, a.stream>>>(gp);
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
-    return (a.type == kF32) ? launch_reduce<float>(gp, ks, a.stream) : launch_reduce<__nv_bfloat16>(gp, ks, a.stream);
+    if (int e2 = debug_sync("row classification", a.stream)) return e2;
+    if (a.classify_only) return 0;
+    const int rc = (a.type == kF32) ? launch_reduce<float>(gp, ks, a.stream) : launch_reduce<__nv_bfloat16>(gp, ks, a.stream);
+    if (rc != 0) return rc;
+    return debug_sync("feature-gradient reduce", a.stream);
 }
 
 }  // namespace hipad

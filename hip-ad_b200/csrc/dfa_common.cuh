@@ -9,6 +9,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <cstdio>
 
 namespace hipad {
 
@@ -108,6 +109,14 @@ struct VecIO<__nv_bfloat16, 8> {
         for (int i = 0; i < 4; ++i)
             u[i] = float_to_bf16_bits(v[2 * i]) | (float_to_bf16_bits(v[2 * i + 1]) << 16);
         *reinterpret_cast<uint4*>(p) = make_uint4(u[0], u[1], u[2], u[3]);
+    }
+};
+
+template <>
+struct VecIO<__nv_bfloat16, 4> {   // 4 channels of a bf16 row (quarter-warp reduce)
+    static __device__ __forceinline__ void store(__nv_bfloat16* p, const float (&v)[4]) {
+        *reinterpret_cast<uint2*>(p) = make_uint2(float_to_bf16_bits(v[0]) | (float_to_bf16_bits(v[1]) << 16),
+                                                  float_to_bf16_bits(v[2]) | (float_to_bf16_bits(v[3]) << 16));
     }
 };
 

@@ -42,7 +42,7 @@ int launch_forward(const FwdArgs& a) {
     const KernelShape ks = pick_shape(a.type, d.C, d.G, al);
     if (!ks.ok || d.cams * d.L > kMaxCamLevels || (long long)d.num_feat * d.C >= (1LL << 30)) return -2;
     const int mode = a.fused ? kFused : kFwd;
-    if (a.fused && ((kSampleWarps * 32) % d.G != 0)) return -2;
+    if (a.fused && (256 % d.G != 0)) return -2;
 
     SampleParams p = {};
     p.feat = a.feat; p.shapes = a.shapes; p.starts = a.starts;
@@ -56,12 +56,13 @@ int launch_forward(const FwdArgs& a) {
     p.PS = (NP + p.S - 1) / p.S;
     const long long grid = rows * p.S;
     if (grid > 0x7fffffffLL) return -2;
-    const size_t smem = sample_smem_for(mode, d, ks, a.type, p.PS);
+    const int warps = choose_sample_warps(grid, d.G);
+    const size_t smem = sample_smem_for(mode, d, ks, a.type, p.PS, warps);
     if (smem > kSampleSmemBudget) return -2;
 
 #define HIPAD_GO(T_, MODE_)                                                                  \
-    return (p.S > 1) ? dispatch_sample<T_, MODE_, true>(p, ks, (int)grid, smem, a.stream)    \
-                     : dispatch_sample<T_, MODE_, false>(p, ks, (int)grid, smem, a.stream)
+    return (p.S > 1) ? dispatch_sample<T_, MODE_, true>(p, ks, warps, (int)grid, smem, a.stream)    \
+                     : dispatch_sample<T_, MODE_, false>(p, ks, warps, (int)grid, smem, a.stream)
     if (a.type == kF32) {
         if (a.fused) HIPAD_GO(float, kFused); else HIPAD_GO(float, kFwd);
     } else {

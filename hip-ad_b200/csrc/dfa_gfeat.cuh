@@ -18,17 +18,14 @@
 //       bucket's record array is decided by an integer atomic cursor; the order INSIDE a key segment is
 //       the stable sample order, which is all the summation order depends on.
 //   dfa_row_classify_kernel one thread per feature row: 4 segment lookups (row (y,x) is corner 1/2/3/4 of
-//       the quads keyed (y,x), (y,x-1), (y-1,x), (y-1,x-1)); rows with 1..kHeavyRow contributions are
-//       appended (warp-aggregated integer atomics) to the LIGHT work list together with their segment
-//       bounds, rows with more to the HEAVY list.  Untouched rows (most of them) cost a few loads.
-//   dfa_gfeat_light_kernel  persistent warps stride over the light list; one warp per row accumulates
-//       coef * w[g] * grad_out[b,a,:] in registers (lane = V channels x NCH chunks, LDG.128) in the
-//       row's fixed order and overwrites the row.  List order is irrelevant for the result (each row is
-//       summed by one warp in sorted-record order) and the stride interleaves coarse and fine levels, so
-//       the load is balanced at warp granularity.
-//   dfa_gfeat_heavy_kernel  rows with > kHeavyRow contributions (coarse levels): persistent CTAs whose
-//       8 warps split one row's contributions into contiguous ranges and combine the partials in warp
-//       order.
+//       the quads keyed (y,x), (y,x-1), (y-1,x), (y-1,x-1)); touched rows are appended (warp-aggregated
+//       integer atomics) to work lists together with their segment bounds: rows with <= kTinyRow
+//       contributions to the tiny list, the others as one PART item per kPart contributions.
+//       Untouched rows (most of them) cost a few loads.
+//   dfa_gfeat_reduce_kernel persistent warps pull items from one dynamic queue: a part item is summed by a
+//       warp (lane = V channels x NCH chunks, LDG.128, loads of 8 contributions in flight), a tiny item
+//       is four rows summed by the four quarters of a warp.  Rows of several parts are combined in part
+//       order by whichever warp finishes last (see the kernel).
 #pragma once
 #include "dfa_common.cuh"
 
@@ -45,12 +42,9 @@ constexpr int kMaxBands = 16;
 constexpr int kScanUnroll = 8;           // independent loads in flight per lane in the band kernel's scans
 constexpr int kSegScale = 8;             // ints of segment table per feature row (upper bound, see seg_offset)
 constexpr int kClassifyThreads = 256;    // rows classified per CTA (one thread each)
-constexpr int kLightWarps = 8;
-constexpr int kLightCtas = 148 * 4;      // persistent CTAs of the light-row kernel
-constexpr int kHeavyWarps = 8;
-constexpr int kHeavyRow = 64;            // contributions above which a row goes to the heavy kernel
-constexpr int kHeavyUnit = 512;          // contributions per heavy work unit (one CTA pass)
-constexpr int kHeavyCtas = 148 * 2;      // persistent CTAs of the heavy-row kernel
+constexpr int kReduceCtas = 148 * 2;     // persistent CTAs (8 warps, 2 per SM) of the reduce kernel
+constexpr int kTinyRow = 8;              // contributions up to which a row is summed by a quarter warp
+constexpr int kPart = 32;                // contributions per part item (longer rows are split into parts)
 constexpr int kMaxChunks = 4096;         // A*P <= 4 Mi samples per batch element
 
 struct GfeatParams {
@@ -67,15 +61,17 @@ struct GfeatParams {
     int* seg;          // [bs][seg_stride]     segment tables (absolute positions inside the bucket's rec[])
     int* cursor;       // [bs][cams*L]         records allocated so far in each bucket
     unsigned long long* sortbuf;  // [bs][cams*L][2][A*P] global ping-pong (bands that exceed shared memory)
-    int4* heavy_list;  // [bs*num_feat + partial slots][4]  work-list entries (kEntryInts), one per heavy unit
-    int4* light_list;  // [bs*num_feat][4]                  work-list entries, one per light row
-    float* partial;    // [partial slots][C]   unit sums of rows with more than one unit
-    int* unit_done;    // [partial slots]      units finished, indexed by a row's first slot
-    int* counters;     // [0] heavy units  [1] light rows  [2] partial slots   (zeroed by the compaction kernel)
+    int4* part_list;   // [bs*num_feat + partial_cap][4]  work-list entries (kEntryInts ints), one per part item
+    int4* tiny_list;   // [bs*num_feat][4]                work-list entries, one per tiny row (tiny_ok only)
+    float* partial;    // [partial_cap][C]     part sums of rows with more than one part
+    int* unit_done;    // [partial_cap]        parts finished, indexed by a row's first slot
+    int* counters;     // [0] part items  [2] partial slots  [3] tiny rows  [4] reduce queue head  (zeroed by the compaction kernel)
+    int partial_cap;
     Dims d;
     int seg_stride;    // ints per batch element in seg
     int n_chunks;
     int NB;            // requested bands per bucket (<= kMaxBands)
+    int tiny_ok;       // shape supported by the quarter-warp kernel (C % 32 == 0, C <= 256, (C/G) % 32 == 0)
 };
 
 __host__ __device__ inline int bits_for(unsigned v) {   // number of bits to represent values < v
@@ -123,7 +119,7 @@ __global__ void __launch_bounds__(kVisThreads) dfa_vis_compact_kernel(const Gfea
 
     if (c == 0 && cam == 0) {
         for (int i = tid; i < d.cams * d.L; i += kVisThreads) p.cursor[(size_t)b_idx * d.cams * d.L + i] = 0;
-        if (b_idx == 0 && tid < 4) p.counters[tid] = 0;
+        if (b_idx == 0 && tid < 8) p.counters[tid] = 0;
     }
     const float2* loc2 = reinterpret_cast<const float2*>(p.loc) + (size_t)b_idx * AP * d.cams + cam;
     const int s_base = c * kVisChunk + warp * kPerWarp;
@@ -449,9 +445,10 @@ __global__ void __launch_bounds__(kSortThreads) dfa_band_sort_kernel(const Gfeat
 }
 
 // ------------------------------------------------------------------------------------------ reduce
-constexpr int kEntryInts = 16;   // work-list entry, shared by the light and the heavy list:
+constexpr int kEntryInts = 16;   // work-list entry, shared by the part and the tiny list:
 //   [0] b*num_feat + row   [1] n (contributions)   [2] b   [3] cam | level << 8 | bucket << 16
-//   [4..7] beg[4]          [8..10] e1, e2, e3      [12] unit | units << 16   [13] first partial slot
+//   [4..7] beg[4]          [8..10] e1, e2, e3      [12] part | parts << 16   [13] first partial slot
+//   [14], [15] contribution range [c_lo, c_hi) of the part
 
 template <int V, int NCH>
 struct RowCtx {
@@ -604,158 +601,151 @@ __global__ void __launch_bounds__(kClassifyThreads) dfa_row_classify_kernel(cons
             n = row_segments(p.seg + (size_t)b_idx * p.seg_stride + seg_offset(st), g, y, x, beg, e1, e2, e3);
         }
     }
-    const bool heavy = n > kHeavyRow, light = n > 0 && !heavy;
+    const bool tiny = p.tiny_ok && n > 0 && n <= kTinyRow;
+    const bool single = n > 0 && !tiny && n <= kPart, multi = n > kPart;
     const int cam = (cl >= 0) ? cl / d.L : 0;
     const int4 q0 = make_int4(b_idx * d.num_feat + row, n, b_idx, cam | ((cl - cam * d.L) << 8) | (cl << 16));
     const int4 q1 = make_int4(beg[0], beg[1], beg[2], beg[3]);
     const int4 q2 = make_int4(e1, e2, e3, 0);
-    // light rows: warp-aggregated append, one integer atomic per warp
-    const unsigned bl = __ballot_sync(0xffffffffu, light);
-    int base_l = 0;
-    if (lane == 0 && bl) base_l = atomicAdd(p.counters + 1, __popc(bl));
-    base_l = __shfl_sync(0xffffffffu, base_l, 0);
-    if (light) {
-        int4* e = p.light_list + (size_t)(base_l + __popc(bl & ((1u << lane) - 1u))) * (kEntryInts / 4);
+    const unsigned lt = (1u << lane) - 1u;
+    // tiny rows and single-part rows: warp-aggregated appends, one integer atomic per warp and list
+    const unsigned bt = __ballot_sync(0xffffffffu, tiny), bs1 = __ballot_sync(0xffffffffu, single);
+    int base_t = 0, base_s = 0;
+    if (lane == 0) {
+        if (bt) base_t = atomicAdd(p.counters + 3, __popc(bt));
+        if (bs1) base_s = atomicAdd(p.counters + 0, __popc(bs1));
+    }
+    base_t = __shfl_sync(0xffffffffu, base_t, 0);
+    base_s = __shfl_sync(0xffffffffu, base_s, 0);
+    if (tiny) {
+        int4* e = p.tiny_list + (size_t)(base_t + __popc(bt & lt)) * (kEntryInts / 4);
         e[0] = q0; e[1] = q1; e[2] = q2;
     }
-    // heavy rows: one entry per unit of kHeavyUnit contributions; multi-unit rows get partial-sum slots
-    if (heavy) {
-        const int units = (n + kHeavyUnit - 1) / kHeavyUnit;
-        const int at = atomicAdd(p.counters + 0, units);
-        int slot = -1;
-        if (units > 1) {
-            slot = atomicAdd(p.counters + 2, units);
+    if (single) {
+        int4* e = p.part_list + (size_t)(base_s + __popc(bs1 & lt)) * (kEntryInts / 4);
+        e[0] = q0; e[1] = q1; e[2] = q2;
+        e[3] = make_int4(0 | (1 << 16), -1, 0, n);
+    }
+    // rows with more than kPart contributions: one entry per part, partial-sum slots for the parts
+    if (multi) {
+        int parts = (n + kPart - 1) / kPart;
+        int slot = atomicAdd(p.counters + 2, parts);
+        if (slot + parts > p.partial_cap) {   // out of partial slots (pathological inputs): one warp sums the whole row
+            parts = 1;
+            slot = -1;
+        } else {
             p.unit_done[slot] = 0;
         }
-        for (int u = 0; u < units; ++u) {
-            int4* e = p.heavy_list + (size_t)(at + u) * (kEntryInts / 4);
+        const int at = atomicAdd(p.counters + 0, parts);
+        for (int u = 0; u < parts; ++u) {
+            int4* e = p.part_list + (size_t)(at + u) * (kEntryInts / 4);
             e[0] = q0; e[1] = q1; e[2] = q2;
-            e[3] = make_int4(u | (units << 16), slot, 0, 0);
+            e[3] = make_int4(u | (parts << 16), slot, u * kPart, (parts == 1) ? n : min(n, (u + 1) * kPart));
         }
     }
 }
 
-// grid (kLightCtas), block kLightWarps*32: persistent warps, one light row at a time
-template <typename T, int V, int NCH>
-__global__ void __launch_bounds__(kLightWarps * 32, 2) dfa_gfeat_light_kernel(const GfeatParams p) {
+// One reduce kernel, persistent warps, ONE dynamic queue over all work items (integer atomic; which warp takes
+// which item does not influence any result):
+//   part items  a range of <= kPart contributions of one row, summed by a warp in the row's fixed order.  Rows
+//               with a single part are written directly; parts of longer rows go to partial-sum slots and the
+//               warp that finishes a row's last part adds the slots in part order and writes the row.
+//   tiny items  four rows with <= kTinyRow contributions each, one per QUARTER warp (lane s of a quarter owns
+//               channels (i*8+s)*4.. of every 32-channel chunk i < NQ = C/32; (C/G) % 32 == 0).  Such rows are
+//               pure latency (entry -> records -> grad_out rows); the lever is rows in flight per SM.
+// The next item's index and its list entry are fetched while the current item is processed.
+template <typename T, int V, int NCH, int NQ>
+__global__ void __launch_bounds__(256, 2) dfa_gfeat_reduce_kernel(const GfeatParams p) {
     const Dims d = p.d;
-    const int lane = threadIdx.x & 31;
-    const int n_light = p.counters[1];
-    const int gwarp = blockIdx.x * kLightWarps + (threadIdx.x >> 5), n_warps = gridDim.x * kLightWarps;
+    const int lane = threadIdx.x & 31, sub = lane & 7, quarter = lane >> 3;
+    const int n_parts = p.counters[0];
+    const int n_tiny = (NQ > 0) ? p.counters[3] : 0;
+    const int total = n_parts + (n_tiny + 3) / 4;
+    const int n_cl = d.cams * d.L;
+    const size_t AP = (size_t)d.A * d.P;
 
     LaneMap<V, NCH> lm;
     lm.init(d.C, d.G);
     RowCtx<V, NCH> cx;
     cx.c_bytes = (unsigned)d.C * 4u;
-    cx.w_stride_bytes = (unsigned)(d.cams * d.L * d.G) * 4u;
-    const int* list = reinterpret_cast<const int*>(p.light_list);
-    int field = (gwarp < n_light && lane < 12) ? __ldg(list + (size_t)gwarp * kEntryInts + lane) : 0;
-#pragma unroll 1
-    for (int i = gwarp; i < n_light; i += n_warps) {
-        const int cur = field;
-        if (i + n_warps < n_light && lane < 12) field = __ldg(list + (size_t)(i + n_warps) * kEntryInts + lane);   // prefetch
-        const int grow = __shfl_sync(0xffffffffu, cur, 0);
-        const int rn = __shfl_sync(0xffffffffu, cur, 1);
-        row_ctx_from_entry<V, NCH>(cx, lm, p, __shfl_sync(0xffffffffu, cur, 2), __shfl_sync(0xffffffffu, cur, 3));
-#pragma unroll
-        for (int k = 0; k < 4; ++k) cx.beg[k] = __shfl_sync(0xffffffffu, cur, 4 + k);
-        cx.e1 = __shfl_sync(0xffffffffu, cur, 8);
-        cx.e2 = __shfl_sync(0xffffffffu, cur, 9);
-        cx.e3 = __shfl_sync(0xffffffffu, cur, 10);
-        float acc[NCH][V];
-#pragma unroll
-        for (int j = 0; j < NCH; ++j)
-#pragma unroll
-            for (int e = 0; e < V; ++e) acc[j][e] = 0.f;
-        accumulate_row<V, NCH>(cx, 0, rn, acc);
-        T* dst = reinterpret_cast<T*>(p.g_feat) + (size_t)grow * d.C;
-#pragma unroll
-        for (int j = 0; j < NCH; ++j)
-            if (lm.act[j]) VecIO<T, V>::store(dst + lm.ch[j], acc[j]);
+    cx.w_stride_bytes = (unsigned)(n_cl * d.G) * 4u;
+    const int* plist = reinterpret_cast<const int*>(p.part_list);
+    const int* tlist = reinterpret_cast<const int*>(p.tiny_list);
+
+    // entry words of item `idx`: part items -> lane j holds word j (j < 16); tiny items -> the lanes of quarter
+    // q hold words sub and sub + 8 of row 4*t + q
+    auto fetch = [&](int idx, int& fa, int& fb) {
+        fa = 0; fb = 0;
+        if (idx < n_parts) {
+            if (lane < kEntryInts) fa = __ldg(plist + (size_t)idx * kEntryInts + lane);
+        } else if (idx < total) {
+            const int r = (idx - n_parts) * 4 + quarter;
+            if (r < n_tiny) {
+                fa = __ldg(tlist + (size_t)r * kEntryInts + sub);
+                fb = __ldg(tlist + (size_t)r * kEntryInts + 8 + sub);
+            }
+        }
+    };
+
+    int cur = 0, nxt = 0;
+    if (lane == 0) {
+        cur = atomicAdd(p.counters + 4, 1);
+        nxt = atomicAdd(p.counters + 4, 1);
     }
-}
+    cur = __shfl_sync(0xffffffffu, cur, 0);
+    int fa, fb;
+    fetch(cur, fa, fb);
+#pragma unroll 1
+    while (cur < total) {
+        nxt = __shfl_sync(0xffffffffu, nxt, 0);
+        int na, nb2;
+        fetch(nxt, na, nb2);                                   // in flight while this item is processed
+        int after = 0;
+        if (lane == 0) after = atomicAdd(p.counters + 4, 1);   // likewise
 
-// grid (kHeavyCtas), block kHeavyWarps*32: persistent CTAs stride over the heavy UNITS.  A unit is up to
-// kHeavyUnit consecutive contributions of one row, split evenly over the 8 warps; warp 0 adds the 8
-// partials in warp order.  Single-unit rows are written directly; units of a longer row go to
-// partial-sum slots and the CTA that finishes last adds them in unit order (which CTA that is does not
-// influence the result).
-template <typename T, int V, int NCH>
-__global__ void __launch_bounds__(kHeavyWarps * 32, 2) dfa_gfeat_heavy_kernel(const GfeatParams p) {
-    constexpr int CPAD = NCH * 32 * V;
-    const Dims d = p.d;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    __shared__ __align__(16) float red[kHeavyWarps * CPAD];
-    __shared__ int s_ent[kEntryInts];
-
-    const int n_units = p.counters[0];
-    LaneMap<V, NCH> lm;
-    lm.init(d.C, d.G);
-    RowCtx<V, NCH> cx;
-    cx.c_bytes = (unsigned)d.C * 4u;
-    cx.w_stride_bytes = (unsigned)(d.cams * d.L * d.G) * 4u;
-
-    for (int i = blockIdx.x; i < n_units; i += gridDim.x) {
-        if (tid < kEntryInts) s_ent[tid] = reinterpret_cast<const int*>(p.heavy_list)[(size_t)i * kEntryInts + tid];
-        __syncthreads();
-        const int grow = s_ent[0], n = s_ent[1];
-        const int u = s_ent[12] & 0xffff, units = s_ent[12] >> 16, slot = s_ent[13];
-        row_ctx_from_entry<V, NCH>(cx, lm, p, s_ent[2], s_ent[3]);
+        if (cur < n_parts) {
+            // ------------------------------------------------------------------ part item
+            const int grow = __shfl_sync(0xffffffffu, fa, 0);
+            row_ctx_from_entry<V, NCH>(cx, lm, p, __shfl_sync(0xffffffffu, fa, 2), __shfl_sync(0xffffffffu, fa, 3));
 #pragma unroll
-        for (int k = 0; k < 4; ++k) cx.beg[k] = s_ent[4 + k];
-        cx.e1 = s_ent[8]; cx.e2 = s_ent[9]; cx.e3 = s_ent[10];
-
-        const int u_lo = u * kHeavyUnit, u_hi = min(n, u_lo + kHeavyUnit);
-        int per = (u_hi - u_lo + kHeavyWarps - 1) / kHeavyWarps;
-        per = (per + 7) & ~7;                      // whole load batches per warp
-        const int c_lo = min(u_hi, u_lo + warp * per), c_hi = min(u_hi, c_lo + per);
-        float acc[NCH][V];
-#pragma unroll
-        for (int j = 0; j < NCH; ++j)
-#pragma unroll
-            for (int q = 0; q < V; ++q) acc[j][q] = 0.f;
-        if (c_lo < c_hi) accumulate_row<V, NCH>(cx, c_lo, c_hi, acc);
-#pragma unroll
-        for (int j = 0; j < NCH; ++j)
-#pragma unroll
-            for (int q = 0; q < V; ++q) red[warp * CPAD + (j * 32 + lane) * V + q] = acc[j][q];
-        __syncthreads();
-        if (warp == 0) {
-            float sum[NCH][V];
+            for (int k = 0; k < 4; ++k) cx.beg[k] = __shfl_sync(0xffffffffu, fa, 4 + k);
+            cx.e1 = __shfl_sync(0xffffffffu, fa, 8);
+            cx.e2 = __shfl_sync(0xffffffffu, fa, 9);
+            cx.e3 = __shfl_sync(0xffffffffu, fa, 10);
+            const int up = __shfl_sync(0xffffffffu, fa, 12), slot = __shfl_sync(0xffffffffu, fa, 13);
+            const int c_lo = __shfl_sync(0xffffffffu, fa, 14), c_hi = __shfl_sync(0xffffffffu, fa, 15);
+            const int u = up & 0xffff, parts = up >> 16;
+            float acc[NCH][V];
 #pragma unroll
             for (int j = 0; j < NCH; ++j)
 #pragma unroll
-                for (int q = 0; q < V; ++q) {
-                    float s = 0.f;
-#pragma unroll
-                    for (int ww = 0; ww < kHeavyWarps; ++ww) s += red[ww * CPAD + (j * 32 + lane) * V + q];
-                    sum[j][q] = s;
-                }
-            bool write_row = units == 1;
-            if (units > 1) {
+                for (int e = 0; e < V; ++e) acc[j][e] = 0.f;
+            accumulate_row<V, NCH>(cx, c_lo, c_hi, acc);
+            bool write_row = parts == 1;
+            if (parts > 1) {
                 float* mine = p.partial + (size_t)(slot + u) * d.C;
 #pragma unroll
                 for (int j = 0; j < NCH; ++j)
-                    if (lm.act[j]) VecIO<float, V>::store(mine + lm.ch[j], sum[j]);
+                    if (lm.act[j]) VecIO<float, V>::store(mine + lm.ch[j], acc[j]);
                 __threadfence();
                 __syncwarp();
                 int old = 0;
                 if (lane == 0) old = atomicAdd(p.unit_done + slot, 1);
                 old = __shfl_sync(0xffffffffu, old, 0);
-                if (old == units - 1) {        // every unit of this row is in memory: add them in unit order
+                if (old == parts - 1) {        // every part of this row is in memory: add them in part order
                     __threadfence();
                     write_row = true;
 #pragma unroll
                     for (int j = 0; j < NCH; ++j)
 #pragma unroll
-                        for (int q = 0; q < V; ++q) sum[j][q] = 0.f;
-                    for (int uu = 0; uu < units; ++uu) {
+                        for (int e = 0; e < V; ++e) acc[j][e] = 0.f;
+                    for (int uu = 0; uu < parts; ++uu) {
                         const float* part = p.partial + (size_t)(slot + uu) * d.C;
 #pragma unroll
                         for (int j = 0; j < NCH; ++j) {
                             if (!lm.act[j]) continue;
 #pragma unroll
-                            for (int q = 0; q < V; ++q) sum[j][q] += __ldcg(part + lm.ch[j] + q);
+                            for (int e = 0; e < V; ++e) acc[j][e] += __ldcg(part + lm.ch[j] + e);
                         }
                     }
                 }
@@ -764,10 +754,88 @@ __global__ void __launch_bounds__(kHeavyWarps * 32, 2) dfa_gfeat_heavy_kernel(co
                 T* dst = reinterpret_cast<T*>(p.g_feat) + (size_t)grow * d.C;
 #pragma unroll
                 for (int j = 0; j < NCH; ++j)
-                    if (lm.act[j]) VecIO<T, V>::store(dst + lm.ch[j], sum[j]);
+                    if (lm.act[j]) VecIO<T, V>::store(dst + lm.ch[j], acc[j]);
+            }
+        } else if constexpr (NQ > 0) {
+            // ------------------------------------------------------------------ tiny item (4 rows)
+            const bool live = (cur - n_parts) * 4 + quarter < n_tiny;    // a dead quarter walks sample 0 at coefficient 0
+            const int grow = __shfl_sync(0xffffffffu, fa, 0, 8);
+            const int n_ent = __shfl_sync(0xffffffffu, fa, 1, 8);   // every lane takes part in the shuffle
+            const int n = live ? n_ent : 0;
+            const int b_idx = __shfl_sync(0xffffffffu, fa, 2, 8), packed = __shfl_sync(0xffffffffu, fa, 3, 8);
+            const int b1 = __shfl_sync(0xffffffffu, fa, 4, 8), b2 = __shfl_sync(0xffffffffu, fa, 5, 8);
+            const int b3 = __shfl_sync(0xffffffffu, fa, 6, 8), b4 = __shfl_sync(0xffffffffu, fa, 7, 8);
+            const int e1 = __shfl_sync(0xffffffffu, fb, 0, 8), e2 = __shfl_sync(0xffffffffu, fb, 1, 8);
+            const int e3 = __shfl_sync(0xffffffffu, fb, 2, 8);
+            const int cam = packed & 0xff, l = (packed >> 8) & 0xff, rcl = packed >> 16;
+            const int4* rec = p.rec + ((size_t)b_idx * n_cl + rcl) * AP;
+            const char* wts =
+                reinterpret_cast<const char*>(p.weights + (((size_t)b_idx * AP * d.cams + cam) * d.L + l) * d.G);
+            const char* gout = reinterpret_cast<const char*>(p.grad_out + (size_t)b_idx * d.A * d.C + sub * 4);
+            const int gd = d.C / d.G;
+
+            // lane `sub` holds contribution `sub` of its quarter's row (clamped onto the last one, coefficient 0)
+            unsigned go_off = 0, w_off = 0;
+            float coef = 0.f;
+            if (n > 0) {
+                const int v = min(sub, n - 1);
+                const int k = (v >= e1) + (v >= e2) + (v >= e3);
+                const int first = (k == 0) ? 0 : (k == 1) ? e1 : (k == 2) ? e2 : e3;
+                const int bk = (k == 0) ? b1 : (k == 1) ? b2 : (k == 2) ? b3 : b4;
+                const int4 e = __ldg(rec + bk + (v - first));
+                const float lh = __int_as_float(e.z), lw = __int_as_float(e.w);
+                const float hh = 1.f - lh, hw = 1.f - lw;    // same expressions as quad_setup()
+                coef = (k == 0) ? hh * hw : (k == 1) ? hh * lw : (k == 2) ? lh * hw : lh * lw;
+                if (sub >= n) coef = 0.f;
+                go_off = (unsigned)e.y * cx.c_bytes;
+                w_off = (unsigned)e.x * cx.w_stride_bytes;
+            }
+            const int n_max = __reduce_max_sync(0xffffffffu, n);
+            constexpr int NQ1 = (NQ > 0) ? NQ : 1;
+            float acc[NQ1][4];
+#pragma unroll
+            for (int i = 0; i < NQ1; ++i)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) acc[i][q] = 0.f;
+            for (int m0 = 0; m0 < n_max; m0 += 2) {
+                float4 g[2][NQ1];
+                float wg[2][NQ1];
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const int m = min(m0 + u, 7);
+                    const unsigned go_m = __shfl_sync(0xffffffffu, go_off, m, 8);
+                    const unsigned w_m = __shfl_sync(0xffffffffu, w_off, m, 8);
+                    const float cf = __shfl_sync(0xffffffffu, coef, m, 8);
+                    const char* g0 = gout + go_m;
+                    const float* w0 = reinterpret_cast<const float*>(wts + w_m);
+#pragma unroll
+                    for (int i = 0; i < NQ1; ++i) {
+                        g[u][i] = __ldg(reinterpret_cast<const float4*>(g0 + i * 128));
+                        wg[u][i] = __ldg(w0 + (i * 32) / gd) * cf;
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 2; ++u)
+#pragma unroll
+                    for (int i = 0; i < NQ1; ++i) {
+                        const float2 w2 = make_float2(wg[u][i], wg[u][i]);
+                        const float2 lo =
+                            __ffma2_rn(w2, make_float2(g[u][i].x, g[u][i].y), make_float2(acc[i][0], acc[i][1]));
+                        const float2 hi =
+                            __ffma2_rn(w2, make_float2(g[u][i].z, g[u][i].w), make_float2(acc[i][2], acc[i][3]));
+                        acc[i][0] = lo.x; acc[i][1] = lo.y; acc[i][2] = hi.x; acc[i][3] = hi.y;
+                    }
+            }
+            if (live) {
+                T* dst = reinterpret_cast<T*>(p.g_feat) + (size_t)grow * d.C + sub * 4;
+#pragma unroll
+                for (int i = 0; i < NQ1; ++i) VecIO<T, 4>::store(dst + i * 32, acc[i]);
             }
         }
-        __syncthreads();
+        cur = nxt;
+        fa = na;
+        fb = nb2;
+        nxt = after;
     }
 }
 

@@ -57,10 +57,12 @@ struct BwdArgs {
     size_t workspace_bytes;
     cudaStream_t stream;
     int stage_mask;   // bit0 sample-major (g_w,g_loc) + zero fill of g_feat, bit1 compaction + band sort, bit2 reduce
+    bool classify_only;        // debugging: stop after the row classification (stage bit 4 without the reduce)
     bool separate_zero_fill;   // measurement: never fold the zero fill into the sample-major kernel
 };
 int launch_backward(const BwdArgs& a);
 size_t backward_workspace_bytes(const Dims& d);
+size_t backward_counters_offset(const Dims& d);   // debugging: where the 8 work counters live in the workspace
 
 int launch_indices(int32_t* idx, const int* shapes, const int* starts, const float* loc, int bs, int cams, int L,
                    int A, int P, cudaStream_t stream);

@@ -4,7 +4,7 @@ set -u
 TAG=${1:-quick}
 OUT=gpurun_out/$TAG
 mkdir -p $OUT
-timeout 900 python -m pytest tests -m gpu -x -q > $OUT/pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a $OUT/status.txt
+timeout 600 python -m pytest tests -m gpu -x -q -p timeout --timeout 60 > $OUT/pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a $OUT/status.txt
 tail -15 $OUT/pytest_gpu.log
 for k in det map plan ego; do timeout 120 python profiles/run_kernels.py $k 4 1 2>&1 | tail -2 | tee -a $OUT/kernels.txt; done
 timeout 120 python profiles/run_kernels.py det 3 4 2>&1 | tail -1 | tee -a $OUT/kernels.txt
