@@ -191,8 +191,13 @@ def gpu_arm(args):
     starts_d = torch.from_numpy(starts).to(dev)
     dims = lambda c: (bs, CAMS, F, C, L, c["A"], c["P"], G)
     ws_bytes = max(lib.hipad_dfa_backward_workspace_bytes(*dims(c)) for c in calls)
-    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-    g_feat = torch.empty_like(feat)   # one buffer reused by every call of the step (written in full each time)
+    # One workspace and one dense g_feat buffer per MODALITY (reused across layers, written in full by every call):
+    # the four calls of a decoder layer are independent, so with --streams 4 they run as parallel graph branches.
+    n_lanes = 1 if args.streams <= 1 else len(MODALITIES)
+    ws_l = [torch.empty(ws_bytes, dtype=torch.uint8, device=dev) for _ in range(n_lanes)]
+    g_feat_l = [torch.empty_like(feat) for _ in range(n_lanes)]
+    lane_of = {m[0]: (i % n_lanes) for i, m in enumerate(MODALITIES)}
+    ws, g_feat = ws_l[0], g_feat_l[0]
     total_fwd = total_bwd = 0
     for c in calls:
         c["loc_d"] = torch.from_numpy(c["loc"]).to(dev)
@@ -213,16 +218,45 @@ def gpu_arm(args):
                           c["loc_d"].data_ptr(), c["w_d"].data_ptr(), *dims(c), stream), "forward")
 
     def bwd_call(c, stream, mask=7):
+        lane = lane_of[c["kind"]]
         _lib.check(lib.hipad_dfa_backward_stages(
             1 if bf16 else 0, mask, feat.data_ptr(), shapes_d.data_ptr(), starts_d.data_ptr(),
-            c["loc_d"].data_ptr(), c["w_d"].data_ptr(), c["go_d"].data_ptr(), g_feat.data_ptr(),
-            c["g_loc_d"].data_ptr(), c["g_w_d"].data_ptr(), *dims(c), ws.data_ptr(), ws_bytes, stream), "backward")
+            c["loc_d"].data_ptr(), c["w_d"].data_ptr(), c["go_d"].data_ptr(), g_feat_l[lane].data_ptr(),
+            c["g_loc_d"].data_ptr(), c["g_w_d"].data_ptr(), *dims(c), ws_l[lane].data_ptr(), ws_bytes, stream), "backward")
 
-    def issue_step(stream):
-        for c in calls:                 # decoder forward: 6 layers x 4 modalities
-            fwd_call(c, stream)
-        for c in reversed(calls):       # autograd order
-            bwd_call(c, stream)
+    side = [torch.cuda.Stream(device=dev) for _ in range(n_lanes - 1)]
+
+    def layer_group(group, fn, main):
+        # the modality calls of one decoder layer: serial on `main`, or one per stream (fork / join with events,
+        # which CUDA-graph capture turns into parallel branches)
+        if n_lanes == 1:
+            for c in group:
+                fn(c, main.cuda_stream)
+            return
+        fork = torch.cuda.Event()
+        fork.record(main)
+        joins = []
+        for c in group:
+            lane = lane_of[c["kind"]]
+            st = main if lane == 0 else side[lane - 1]
+            if st is not main:
+                st.wait_event(fork)
+            fn(c, st.cuda_stream)
+            if st is not main:
+                ev = torch.cuda.Event()
+                ev.record(st)
+                joins.append(ev)
+        for ev in joins:
+            main.wait_event(ev)
+
+    n_mod = len(MODALITIES)
+    layers = [calls[i:i + n_mod] for i in range(0, len(calls), n_mod)]
+
+    def issue_step(main):
+        for group in layers:                    # decoder forward: 6 layers x 4 modalities
+            layer_group(group, fwd_call, main)
+        for group in reversed(layers):          # autograd order
+            layer_group(list(reversed(group)), bwd_call, main)
 
     # per call: forward sample kernel; backward = sample kernel (+ its own zero-fill kernel when the grid is too
     # small to fold the fill in: the ego call), visible compaction, band sort, touched-row reduce, heavy-row reduce
@@ -237,13 +271,13 @@ def gpu_arm(args):
     stream = torch.cuda.Stream(device=dev)
     graph = None
     with torch.cuda.stream(stream):
-        issue_step(stream.cuda_stream)
-        stream.synchronize()
+        issue_step(stream)
+        torch.cuda.synchronize()
         if not args.no_graph:
             try:
                 graph = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(graph, stream=stream):
-                    issue_step(torch.cuda.current_stream().cuda_stream)
+                    issue_step(torch.cuda.current_stream())
             except Exception as e:  # keep measuring, eagerly
                 print("graph capture failed, timing eager launches:", e, file=sys.stderr)
                 graph = None
@@ -253,7 +287,7 @@ def gpu_arm(args):
         if graph is not None:
             graph.replay()
         else:
-            issue_step(torch.cuda.current_stream().cuda_stream)
+            issue_step(torch.cuda.current_stream())
 
     def barrier():
         if world > 1:
@@ -304,15 +338,17 @@ def gpu_arm(args):
             for c in calls:
                 e = c["_ev"]
                 d = [e[i].elapsed_time(e[i + 1]) * 1e3 for i in range(4)]   # microseconds
-                # algorithmic bytes per stage: forward B_fwd; backward sample kernel B_bwd (it also performs the
-                # dense g_feat write); the sort and the touched-row reduce move no algorithmic bytes of their own
-                for name, dur, nb in zip(kern, d, (c["bytes"]["fwd"], c["bytes"]["bwd"], 0, 0)):
+                # algorithmic bytes per stage (a partition of B_fwd + B_bwd): forward B_fwd; backward sample kernel
+                # everything of B_bwd except the touched rows of the dense g_feat write (it zero-fills the rest);
+                # the reduce writes those touched rows; the sort only re-reads locations (no algorithmic bytes)
+                touched = c["bytes"]["U"] * C * elem
+                for name, dur, nb in zip(kern, d, (c["bytes"]["fwd"], c["bytes"]["bwd"] - touched, 0, touched)):
                     kern[name].append(dur)
                     kbytes[name].append(nb)
                 m = per_mod.setdefault(c["kind"], dict(fwd_us=[], bwd_us=[], bytes=c["bytes"]))
                 m["fwd_us"].append(d[0]); m["bwd_us"].append(d[1] + d[2] + d[3])
     share = {k: float(np.sum(v)) for k, v in kern.items()}
-    dominant = max(share, key=share.get)
+    dominant = max((k for k in share if np.sum(kbytes[k]) > 0), key=share.get)
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -422,6 +458,7 @@ def gpu_arm(args):
                                    "plan 480x90 + ego 1x13), 6 cams, 4 levels of 352x640, C=256, G=8, fwd+bwd",
                        "bs_per_gpu": bs, "feature_dtype": args.dtype, "parallelism": "batch-sharded x%d" % world,
                        "l2": "256 MiB read sweep (flush) between timed steps", "cuda_graph": graph is not None,
+                       "streams": n_lanes,
                        "locations": "B2D camera geometry, det/map/plan visible fraction ~0.20/0.19/0.13, ego 0"},
             "samples_per_s": round(world * bs / (ms_per_step * 1e-3), 2),
             "algorithmic_bytes_per_step": int(step_bytes),
@@ -513,6 +550,8 @@ def main():
     ap.add_argument("--bs", type=int, default=1, help="samples per GPU")
     ap.add_argument("--dtype", default="f32", choices=["f32", "bf16"], help="feature-map storage type")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--streams", type=int, default=4,
+                    help="4: the four modality calls of a decoder layer run as parallel branches; 1: strictly serial")
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of CPU baseline work")
