@@ -25,6 +25,7 @@ _SIGNATURES = {
     "hipad_dfa_sample_indices": ([_p] * 4 + [_i] * 5 + [_p], _i),
     "hipad_dfa_fused_forward_f32": ([_p] * 9 + _DIMS8 + [_p], _i),
     "hipad_dfa_fused_forward_bf16": ([_p] * 9 + _DIMS8 + [_p], _i),
+    "hipad_dfa_format_features": ([_i, _i, _i, _p, _p, _p, _i, _i, _i, _i, _p], _i),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 

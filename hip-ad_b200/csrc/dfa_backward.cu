@@ -18,7 +18,7 @@ constexpr size_t kAlign = 256;
 inline size_t align_up(size_t v) { return (v + kAlign - 1) / kAlign * kAlign; }
 
 struct WorkspaceLayout {
-    size_t vis_id, vis_xy, vis_cnt, rec, seg, cursor, sortbuf, part_list, tiny_list, partial, unit_done, counters, total;
+    size_t vis_id, vis_xy, vis_cnt, band_cnt, rec, seg, cursor, sortbuf, part_list, tiny_list, partial, unit_done, counters, total;
     size_t partial_slots;
     int seg_stride, n_chunks;
 };
@@ -33,6 +33,7 @@ WorkspaceLayout workspace_layout(const Dims& d) {
     w.vis_id = off;  off += align_up((size_t)d.bs * d.cams * AP * sizeof(int));
     w.vis_xy = off;  off += align_up((size_t)d.bs * d.cams * AP * sizeof(float2));
     w.vis_cnt = off; off += align_up((size_t)d.bs * d.cams * w.n_chunks * sizeof(int));
+    w.band_cnt = off; off += align_up((size_t)d.bs * d.cams * w.n_chunks * d.L * kMaxBands * sizeof(int));
     w.rec = off;     off += align_up((size_t)d.bs * n_cl * AP * sizeof(int4));
     w.seg = off;     off += align_up((size_t)d.bs * w.seg_stride * sizeof(int));
     w.cursor = off;  off += align_up((size_t)d.bs * n_cl * sizeof(int));
@@ -149,6 +150,7 @@ int launch_backward(const BwdArgs& a) {
     gp.vis_id = reinterpret_cast<int*>(ws + wl.vis_id);
     gp.vis_xy = reinterpret_cast<float2*>(ws + wl.vis_xy);
     gp.vis_cnt = reinterpret_cast<int*>(ws + wl.vis_cnt);
+    gp.band_cnt = reinterpret_cast<int*>(ws + wl.band_cnt);
     gp.rec = reinterpret_cast<int4*>(ws + wl.rec);
     gp.seg = reinterpret_cast<int*>(ws + wl.seg);
     gp.cursor = reinterpret_cast<int*>(ws + wl.cursor);

@@ -57,6 +57,7 @@ struct GfeatParams {
     int* vis_id;       // [bs][cams][A*P]      compacted visible sample ids, chunk c at [c*kVisChunk, ...)
     float2* vis_xy;    // [bs][cams][A*P]      their locations
     int* vis_cnt;      // [bs][cams][n_chunks] visible samples per chunk
+    int* band_cnt;     // [bs][cams][n_chunks][L][kMaxBands] of them, per level, the ones whose quad row falls into each band
     int4* rec;         // [bs][cams*L][A*P]    sorted records {sample, anchor, lh, lw}
     int* seg;          // [bs][seg_stride]     segment tables (absolute positions inside the bucket's rec[])
     int* cursor;       // [bs][cams*L]         records allocated so far in each bucket
@@ -116,11 +117,13 @@ __global__ void __launch_bounds__(kVisThreads) dfa_vis_compact_kernel(const Gfea
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int AP = d.A * d.P;
     __shared__ int s_wcnt[kWarps];
+    __shared__ int s_bc[kMaxCamLevels * kMaxBands];     // [level][band] counts of this chunk
 
     if (c == 0 && cam == 0) {
         for (int i = tid; i < d.cams * d.L; i += kVisThreads) p.cursor[(size_t)b_idx * d.cams * d.L + i] = 0;
         if (b_idx == 0 && tid < 8) p.counters[tid] = 0;
     }
+    for (int i = tid; i < d.L * kMaxBands; i += kVisThreads) s_bc[i] = 0;
     const float2* loc2 = reinterpret_cast<const float2*>(p.loc) + (size_t)b_idx * AP * d.cams + cam;
     const int s_base = c * kVisChunk + warp * kPerWarp;
     float2 xy[kIter];
@@ -136,6 +139,19 @@ __global__ void __launch_bounds__(kVisThreads) dfa_vis_compact_kernel(const Gfea
     }
     if (lane == 0) s_wcnt[warp] = cnt;
     __syncthreads();
+    // per level: which band of quad rows each visible sample falls into (the band kernel's work split), counted
+    // here so that the band kernel needs a single pass over the compacted list
+    for (int l = 0; l < d.L; ++l) {
+        const int h = __ldg(p.shapes + (cam * d.L + l) * 2), w = __ldg(p.shapes + (cam * d.L + l) * 2 + 1);
+        const Bands g = band_geometry(h, w, p.NB);
+#pragma unroll
+        for (int it = 0; it < kIter; ++it) {
+            if ((bal[it] >> lane) & 1u) {
+                const int qr = __float2int_rd(__fmaf_rn(xy[it].y, (float)h, -0.5f)) + 1;   // quad_setup()'s h_low + 1
+                atomicAdd(&s_bc[l * kMaxBands + qr / g.RB], 1);
+            }
+        }
+    }
     int pos = 0, total = 0;
 #pragma unroll
     for (int w = 0; w < kWarps; ++w) {
@@ -154,6 +170,9 @@ __global__ void __launch_bounds__(kVisThreads) dfa_vis_compact_kernel(const Gfea
         pos += __popc(bal[it]);
     }
     if (tid == 0) p.vis_cnt[((size_t)b_idx * d.cams + cam) * p.n_chunks + c] = total;
+    __syncthreads();
+    int* bc = p.band_cnt + (((size_t)b_idx * d.cams + cam) * p.n_chunks + c) * d.L * kMaxBands;
+    for (int i = tid; i < d.L * kMaxBands; i += kVisThreads) bc[i] = s_bc[i];
 }
 
 // ------------------------------------------------------------------------------------------ band sort
@@ -308,39 +327,14 @@ __device__ void band_sort_body(const GfeatParams& p, const BandCtx& bc, W* a, W*
     }
 
     // seg[k] = first record (absolute position in the bucket) whose key >= k, k = 0..K (K = sentinel):
-    //   fill with the end, mark segment starts, then a suffix-min scan closes the gaps of empty keys.
-    const int end_pos = bc.base + bc.n;
-    for (int k = tid; k <= bc.K; k += kSortThreads) seg_band[k] = end_pos;
-    __syncthreads();
-    for (int i = tid; i < bc.n; i += kSortThreads) {
-        const unsigned key = (unsigned)(sorted[i] >> bc.vb);
-        if (i == 0 || (unsigned)(sorted[i - 1] >> bc.vb) != key) seg_band[key] = bc.base + i;
-    }
-    __syncthreads();
-    {
-        const int per = (bc.K + 1 + kSortThreads - 1) / kSortThreads;
-        const int lo = min(bc.K + 1, tid * per), hi = min(bc.K + 1, lo + per);
-        int run = 0x7fffffff;
-        for (int k = hi - 1; k >= lo; --k) run = min(run, seg_band[k]);
-        int v = run;   // inclusive suffix-min over the lanes of this warp
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int t = __shfl_down_sync(0xffffffffu, v, o);
-            if (lane + o < 32) v = min(v, t);
+    // a lower-bound search in the sorted words per key -- no fill / mark / scan phases, no barriers
+    for (int k = tid; k <= bc.K; k += kSortThreads) {
+        int lo = 0, hi = bc.n;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if ((int)(sorted[mid] >> bc.vb) < k) lo = mid + 1; else hi = mid;
         }
-        int* s_wmin = reinterpret_cast<int*>(tot);          // kSortWarps ints of scratch
-        __syncthreads();
-        if (lane == 0) s_wmin[warp] = v;
-        __syncthreads();
-        int after = 0x7fffffff;                             // min over later warps
-        for (int ww = warp + 1; ww < kSortWarps; ++ww) after = min(after, s_wmin[ww]);
-        int excl = __shfl_down_sync(0xffffffffu, v, 1);     // suffix-min of the lanes after this one
-        if (lane == 31) excl = 0x7fffffff;
-        int carry = min(excl, after);
-        for (int k = hi - 1; k >= lo; --k) {
-            carry = min(carry, seg_band[k]);
-            seg_band[k] = carry;
-        }
+        seg_band[k] = bc.base + lo;
     }
 }
 
@@ -375,28 +369,11 @@ __global__ void __launch_bounds__(kSortThreads) dfa_band_sort_kernel(const Gfeat
     int* s_coff = s_misc + 16;
     unsigned char* data = reinterpret_cast<unsigned char*>(s_coff + ((p.n_chunks + 3) & ~3));
 
-    // in-band samples per chunk (same quad_setup as every other kernel)
-    const size_t cam_list = ((size_t)b_idx * d.cams + cam) * AP;
-    const int* cnts = p.vis_cnt + ((size_t)b_idx * d.cams + cam) * p.n_chunks;
-    for (int c = warp; c < p.n_chunks; c += kSortWarps) {
-        const int cnt = __ldg(cnts + c);
-        const float2* xys = p.vis_xy + cam_list + (size_t)c * kVisChunk;
-        int m = 0;
-        for (int i0 = 0; i0 < cnt; i0 += 32 * kScanUnroll) {   // kScanUnroll independent loads in flight per lane
-            float y[kScanUnroll];
-#pragma unroll
-            for (int u = 0; u < kScanUnroll; ++u) {
-                const int i = i0 + u * 32 + lane;
-                y[u] = (i < cnt) ? __ldg(reinterpret_cast<const float*>(xys + i) + 1) : -1.f;   // -1: never in a band
-            }
-#pragma unroll
-            for (int u = 0; u < kScanUnroll; ++u) {
-                const int qr = __float2int_rd(__fmaf_rn(y[u], (float)h, -0.5f)) + 1;
-                m += (qr >= bc.q0 && qr < bc.q1) ? 1 : 0;
-            }
-        }
-        m = __reduce_add_sync(0xffffffffu, m);
-        if (lane == 0) s_coff[c] = m;
+    // in-band samples per chunk, counted by the compaction kernel
+    {
+        const int l = cl - cam * d.L;
+        const int* bcnt = p.band_cnt + ((size_t)b_idx * d.cams + cam) * p.n_chunks * d.L * kMaxBands + l * kMaxBands + band;
+        for (int c = tid; c < p.n_chunks; c += kSortThreads) s_coff[c] = __ldg(bcnt + (size_t)c * d.L * kMaxBands);
     }
     __syncthreads();
     if (warp == 0) {    // exclusive scan over the chunks

@@ -10,6 +10,8 @@ import torch
 from .deformable_aggregation import (  # noqa: F401
     DeformableAggregationFunction,
     DeformableAggregationFunctionA800,
+    FeatureMapsFormatFunction,
+    format_feature_levels,
     fused_deformable_aggregation,
     sample_indices,
 )
@@ -82,9 +84,15 @@ def feature_maps_format(feature_maps, inverse=False):
 
     bs, num_cams = feature_maps[0].shape[:2]
     level_hw = [[int(f.shape[-2]), int(f.shape[-1])] for f in feature_maps]
-    col_feats = torch.cat(
-        [f.reshape(bs, num_cams, f.shape[2], -1) for f in feature_maps], dim=-1
-    ).permute(0, 1, 3, 2).flatten(1, 2)
+    f0 = feature_maps[0]
+    if (f0.is_cuda and f0.dtype in (torch.float32, torch.bfloat16) and len(feature_maps) <= 8 and bs * num_cams <= 65535
+            and all(f.is_cuda and f.dtype == f0.dtype and f.dim() == 5 for f in feature_maps)):
+        # one transposing kernel (hipad_dfa_format_features) instead of the reference's two full copies
+        col_feats = format_feature_levels(list(feature_maps))
+    else:   # host tensors / exotic dtypes: the reference's own layout ops (pure data movement, no arithmetic)
+        col_feats = torch.cat(
+            [f.reshape(bs, num_cams, f.shape[2], -1) for f in feature_maps], dim=-1
+        ).permute(0, 1, 3, 2).flatten(1, 2)
     shape_list = [[list(hw) for hw in level_hw] for _ in range(num_cams)]
     start_list, row = [], 0
     for _ in range(num_cams):

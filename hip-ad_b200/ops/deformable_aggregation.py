@@ -146,6 +146,56 @@ def fused_deformable_aggregation(feature_maps, key_points, projection_mat, image
     return (out, loc) if return_locations else out
 
 
+_DTYPE_CODE = {torch.float32: 0, torch.bfloat16: 1}
+
+
+def _format_call(levels, col, inverse):
+    """levels: list of contiguous [bs, cams, C, H, W] CUDA tensors; col: [bs, cams*sum(HW), C].  One kernel."""
+    import ctypes
+    lib = _lib.get()
+    bs, cams, C = levels[0].shape[:3]
+    L = len(levels)
+    ptrs = (ctypes.c_void_p * L)(*[t.data_ptr() for t in levels])
+    hw = (ctypes.c_int32 * (2 * L))(*[int(v) for t in levels for v in t.shape[-2:]])
+    with torch.cuda.device(col.device):
+        rc = lib.hipad_dfa_format_features(_DTYPE_CODE[levels[0].dtype], _DTYPE_CODE[col.dtype], int(inverse),
+                                           ctypes.cast(ptrs, ctypes.c_void_p), ctypes.cast(hw, ctypes.c_void_p),
+                                           col.data_ptr(), bs, cams, C, L, torch.cuda.current_stream().cuda_stream)
+    _lib.check(rc, "hipad_dfa_format_features")
+
+
+class FeatureMapsFormatFunction(Function):
+    """levels [bs, cams, C, H_l, W_l] (f32 or bf16, CUDA) -> col_feats [bs, cams*sum(H_l*W_l), C] in ONE transposing
+    pass (``ops/__init__.py:74-103`` of the reference does cat + permute + flatten = two full copies); the backward
+    is the same kernel run in the other direction.  ``out_dtype`` lets an f32 pyramid be narrowed to bf16 on the way."""
+
+    @staticmethod
+    def forward(ctx, out_dtype, *levels):
+        levels = [t.contiguous() for t in levels]
+        bs, cams, C = levels[0].shape[:3]
+        rows = sum(int(t.shape[-2]) * int(t.shape[-1]) for t in levels)
+        col = torch.empty((bs, cams * rows, C), dtype=out_dtype or levels[0].dtype, device=levels[0].device)
+        _format_call(levels, col, inverse=False)
+        ctx.level_shapes = [tuple(t.shape) for t in levels]
+        ctx.level_dtype = levels[0].dtype
+        return col
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_col):
+        grad_col = grad_col.contiguous()
+        if grad_col.dtype not in _DTYPE_CODE:
+            grad_col = grad_col.float()
+        grads = [torch.empty(shape, dtype=ctx.level_dtype, device=grad_col.device) for shape in ctx.level_shapes]
+        _format_call(grads, grad_col, inverse=True)
+        return (None, *grads)
+
+
+def format_feature_levels(levels, out_dtype=None):
+    """CUDA path of ``feature_maps_format`` for one camera group; returns col_feats."""
+    return FeatureMapsFormatFunction.apply(out_dtype, *levels)
+
+
 def sample_indices(spatial_shape, scale_start_index, sampling_location):
     """int32 [bs, A, P, cams, L, 6] = (valid, h_low, w_low, level_offset, corner_mask, row0) exactly as
     the kernels compute them (the bit-exact integer contract checked against the oracle)."""

@@ -156,6 +156,20 @@ int hipad_dfa_fused_forward_bf16(float *output, const uint16_t *mc_ms_feat,
                                  int num_scale, int num_anchors, int num_pts, int num_groups,
                                  void *stream);
 
+/* ---- feature_maps_format as one transposing pass ----
+ * Replaces the cat + permute + flatten chain of feature_maps_format
+ * (projects/mmdet3d_plugin/ops/__init__.py:74-103; two full copies of every feature map, the second a strided
+ * transpose) by one read and one write:
+ *   level_ptrs  HOST array of num_scale DEVICE pointers, level l = [bs, cams, C, H_l, W_l] contiguous
+ *   level_hw    HOST array [num_scale][2] = (H_l, W_l)
+ *   col_feats   device [bs, cams * sum_l(H_l*W_l), C]  (camera-major, level, row-major pixels, channels last)
+ *   *_dtype     0 = f32, 1 = bf16 (raw uint16 bits); f32 levels may be narrowed to a bf16 col_feats on the way
+ *   inverse     0: levels -> col_feats;  1: col_feats -> levels (the autograd of the format step, and the dense
+ *               form of the inverse=True branch, ops/__init__.py:34-65) */
+int hipad_dfa_format_features(int level_dtype, int col_dtype, int inverse,
+                              void *const *level_ptrs, const int32_t *level_hw, void *col_feats,
+                              int batch_size, int num_cams, int num_embeds, int num_scale, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -21,3 +21,4 @@ n=len(names)//3
 print("$k per-kernel us (last rep):", ", ".join("%s=%.1f"%(a,b) for a,b in names[-n:]))
 PY
 done
+for a in "1 f32" "1 bf16" "4 f32"; do timeout 120 python profiles/run_format.py $a 2>&1 | tail -1 | tee -a $OUT/kernels.txt; done

@@ -394,3 +394,63 @@ def test_error_behaviour(ops, cuda_lib):
                                             dev(case["loc"])[:, :, :, :1], dev(case["weights"]))
     assert cuda_lib.hipad_dfa_forward_f32(None, None, None, None, None, None, 1, 1, 1, 1, 1, 1, 1, 1, None) == -1
     assert cuda_lib.hipad_dfa_backward_workspace_bytes(1, 6, 112200, 256, 4, 900, 13, 8) > 0
+
+
+# ------------------------------------------------------------------------------------- feature_maps_format kernel
+def _torch_format(fmaps):
+    """The reference's own layout ops (ops/__init__.py:74-103): cat over levels, permute, flatten."""
+    bs, cams = fmaps[0].shape[:2]
+    return torch.cat([f.reshape(bs, cams, f.shape[2], -1) for f in fmaps], dim=-1).permute(0, 1, 3, 2).flatten(1, 2)
+
+
+@pytest.mark.parametrize("shape", [
+    (2, 6, 256, [(16, 28), (8, 14), (4, 7), (2, 4)]),
+    (1, 3, 48, [(7, 9), (5, 3)]),                       # C and H*W not multiples of the 64-wide tile
+    (1, 2, 130, [(65, 1), (1, 1), (3, 67)]),
+])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_format_kernel_is_a_pure_copy(ops, shape, dtype):
+    bs, cams, C, levels = shape
+    g = torch.Generator(device="cuda").manual_seed(0)
+    fmaps = [torch.randn((bs, cams, C, h, w), device="cuda", generator=g).to(dtype).requires_grad_(True) for h, w in levels]
+    col, shapes_t, starts_t = ops.feature_maps_format(fmaps)
+    ref = _torch_format([f.detach() for f in fmaps])
+    assert col.dtype == dtype and torch.equal(col, ref)                       # bit-exact: layout only
+    assert shapes_t.tolist() == [[list(hw) for hw in levels]] * cams
+    # autograd of the format step = the same kernel run backwards
+    gcol = torch.randn(col.shape, device="cuda", generator=g).to(dtype)
+    col.backward(gcol)
+    ref_in = [f.detach().clone().requires_grad_(True) for f in fmaps]
+    _torch_format(ref_in).backward(gcol)
+    for f, r in zip(fmaps, ref_in):
+        assert torch.equal(f.grad, r.grad)
+    # zero-copy inverse views still see the same data
+    back = ops.feature_maps_format([col, shapes_t, starts_t], inverse=True)
+    for f, v in zip(fmaps, back[0]):
+        assert torch.equal(f.detach(), v)
+
+
+def test_format_kernel_narrows_to_bf16(ops):
+    g = torch.Generator(device="cuda").manual_seed(1)
+    fmaps = [torch.randn((1, 6, 256, h, w), device="cuda", generator=g) for h, w in [(16, 28), (8, 14)]]
+    col = ops.format_feature_levels(fmaps, out_dtype=torch.bfloat16)
+    assert col.dtype == torch.bfloat16 and torch.equal(col, _torch_format(fmaps).bfloat16())
+
+
+def test_format_feeds_the_op_end_to_end(ops, oracle_mod):
+    """levels -> format kernel -> aggregation -> backward through both: gradients reach the NCHW pyramid."""
+    case = small_case("c256_g8_l4", seed=5)
+    bs, cams, lv, C = 2, 6, [(16, 28), (8, 14), (4, 7), (2, 4)], 256
+    feat = torch.as_tensor(case["feat"]).cuda()                              # [bs, F, C]
+    per_cam = sum(h * w for h, w in lv)
+    blocks = feat.view(bs, cams, per_cam, C).split([h * w for h, w in lv], dim=2)
+    fmaps = [b.permute(0, 1, 3, 2).reshape(bs, cams, C, h, w).contiguous().requires_grad_(True)
+             for b, (h, w) in zip(blocks, lv)]
+    fm = ops.feature_maps_format(fmaps)
+    assert torch.equal(fm[0], feat)
+    out = ops.deformable_aggregation_function(*fm, dev(case["loc"]), dev(case["weights"]))
+    out.backward(dev(case["grad_out"]))
+    r_feat, _, _ = oracle_mod.backward(case["feat"], case["shapes"], case["starts"], case["loc"], case["weights"],
+                                       case["grad_out"])
+    got = torch.cat([f.grad.reshape(bs, cams, C, -1) for f in fmaps], dim=-1).permute(0, 1, 3, 2).flatten(1, 2)
+    assert rel_err(got.cpu().numpy(), r_feat) <= FP32_TOL
