@@ -26,6 +26,8 @@ KernelShape pick_shape(ElemType t, int C, int G, bool aligned16) {
 int choose_slices(long long rows, int pairs, int target_ctas, int bytes_per_pair, int max_slices) {
     int S = 1;
     while (S < 8 && S * 2 <= max_slices && rows * S < target_ctas && pairs / (S * 2) >= 64) S *= 2;
+    const int forced = hipad_env_int("HIPAD_DFA_SLICES", 0);   // A/B knob
+    if (forced > 0 && forced <= max_slices && forced <= 8) S = forced;
     // fixed part of the CTA's shared memory (tables, reduction scratch) is < 48 KB for every supported shape
     const long long budget = (long long)kSampleSmemBudget - 48 * 1024;
     while ((long long)((pairs + S - 1) / S) * bytes_per_pair > budget) {

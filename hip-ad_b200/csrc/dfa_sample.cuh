@@ -30,6 +30,7 @@ namespace cg = cooperative_groups;
 
 enum SampleMode { kFwd = 0, kBwd = 1, kFused = 2 };
 
+
 struct SampleParams {
     const void* feat;
     const int* shapes;

@@ -44,7 +44,8 @@ for r in range(reps):
     e[0].record()
     _lib.check(fwd(out.data_ptr(), feat.data_ptr(), sh.data_ptr(), st.data_ptr(), loc.data_ptr(), w.data_ptr(), *dims, s), "fwd")
     e[1].record()
-    for i, m in enumerate((1, 2, 4)):
+    zmask = 8 if os.environ.get("HIPAD_SEPARATE_ZERO") else 0
+    for i, m in enumerate((1 | zmask, 2, 4)):
         _lib.check(lib.hipad_dfa_backward_stages(int(bf16), m, feat.data_ptr(), sh.data_ptr(), st.data_ptr(), loc.data_ptr(),
                                                  w.data_ptr(), go.data_ptr(), g_feat.data_ptr(), g_loc.data_ptr(),
                                                  g_w.data_ptr(), *dims, ws.data_ptr(), nb, s), "bwd")
