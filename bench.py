@@ -30,6 +30,10 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
+# keep NCCL's "NCCL version ..." banner (NCCL_DEBUG=VERSION) off stdout: rank 0 prints exactly one JSON line
+if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+    os.environ["NCCL_DEBUG"] = "WARN"
+
 MODALITIES = (("det", 900, 13), ("map", 100, 300), ("plan", 480, 90), ("ego", 1, 13))
 LAYERS = 6
 FINAL_HW = (352, 640)
@@ -258,6 +262,20 @@ def gpu_arm(args):
         for group in reversed(layers):          # autograd order
             layer_group(list(reversed(group)), bwd_call, main)
 
+    def issue_step_shared(main):
+        # "next" row f1: ONE dense g_feat for the whole step (all 24 calls read the same feature tensor): the first
+        # backward call writes every row, the others accumulate (hipad_dfa_backward_accumulate_*), serial on `main`
+        for group in layers:
+            layer_group(group, fwd_call, main)
+        first = True
+        for c in reversed(calls):
+            _lib.check(lib.hipad_dfa_backward_stages(
+                1 if bf16 else 0, 7 if first else 7 | 32, feat.data_ptr(), shapes_d.data_ptr(), starts_d.data_ptr(),
+                c["loc_d"].data_ptr(), c["w_d"].data_ptr(), c["go_d"].data_ptr(), g_feat_l[0].data_ptr(),
+                c["g_loc_d"].data_ptr(), c["g_w_d"].data_ptr(), *dims(c), ws_l[0].data_ptr(), ws_bytes, main.cuda_stream),
+                "backward (shared g_feat)")
+            first = False
+
     # per call: forward sample kernel; backward = sample kernel (+ its own zero-fill kernel when the grid is too
     # small to fold the fill in: the ego call), visible compaction, band sort, touched-row reduce, heavy-row reduce
     launches_per_step = sum(1 + 5 + (1 if bs * c["A"] * 8 < 2 * 148 else 0) for c in calls)
@@ -315,6 +333,32 @@ def gpu_arm(args):
     total_ms = max_over_ranks(float(sum(step_ms)), dev)
     ms_per_step = total_ms / args.steps
     value = whole_job_gbs(world, step_bytes, ms_per_step)
+
+    # ---- same step with one shared g_feat buffer (reported beside the headline, never instead of it)
+    shared = None
+    if not args.no_graph:
+        try:
+            with torch.cuda.stream(stream):
+                issue_step_shared(stream)
+                torch.cuda.synchronize()
+                g2 = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g2, stream=stream):
+                    issue_step_shared(torch.cuda.current_stream())
+                for _ in range(3):
+                    flush_l2(); g2.replay()
+                ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+                for a, b in ev2:
+                    flush_l2(); a.record(); g2.replay(); b.record()
+                torch.cuda.synchronize()
+            ms2 = max_over_ranks(float(sum(a.elapsed_time(b) for a, b in ev2)), dev) / args.steps
+            dense = bs * F * C * elem
+            touched = sum(c["bytes"]["U"] * C * elem for c in calls)
+            bytes2 = step_bytes - (len(calls) - 1) * dense + 2 * (touched - calls[-1]["bytes"]["U"] * C * elem)
+            shared = {"ms_per_step": round(ms2, 4), "algorithmic_bytes_per_step": int(bytes2),
+                      "value": round(whole_job_gbs(world, bytes2, ms2), 2), "unit": "GB/s",
+                      "note": "one dense g_feat per step: 1 full write + read-modify-write of the touched rows of the other 23 calls"}
+        except Exception as e:
+            shared = {"error": str(e)[:200]}
 
     # ---- per-kernel timing (CUDA events on the launching stream), for the roofline object
     kern = {"dfa_sample_kernel<fwd>": [], "dfa_sample_kernel<bwd>+zero_fill": [], "dfa_vis_compact+band_sort": [],
@@ -484,7 +528,7 @@ def gpu_arm(args):
             "samples_per_s": round(world * bs / (ms_per_step * 1e-3), 2),
             "algorithmic_bytes_per_step": int(step_bytes),
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
-            "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "shared_gfeat_step": shared,
             "per_call_us": {k: {"fwd": round(float(np.mean(v["fwd_us"])), 1), "bwd": round(float(np.mean(v["bwd_us"])), 1),
                                 "B_fwd": v["bytes"]["fwd"], "B_bwd": v["bytes"]["bwd"], "U_rows": v["bytes"]["U"]}
                             for k, v in per_mod.items()},

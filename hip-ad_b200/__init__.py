@@ -9,8 +9,10 @@ from .ops import (  # noqa: F401
     DeformableAggregationFunctionA800,
     deformable_aggregation_function,
     feature_maps_format,
+    format_feature_levels,
     fused_deformable_aggregation,
     sample_indices,
+    share_feature_gradient,
 )
 from .blocks import (  # noqa: F401
     DeformableFeatureAggregation,

@@ -21,6 +21,8 @@ _SIGNATURES = {
     "hipad_dfa_backward_workspace_bytes": (_DIMS8, ctypes.c_size_t),
     "hipad_dfa_backward_f32": ([_p] * 9 + _DIMS8 + [_p, ctypes.c_size_t, _p], _i),
     "hipad_dfa_backward_bf16": ([_p] * 9 + _DIMS8 + [_p, ctypes.c_size_t, _p], _i),
+    "hipad_dfa_backward_accumulate_f32": ([_p] * 9 + _DIMS8 + [_p, ctypes.c_size_t, _p], _i),
+    "hipad_dfa_backward_accumulate_bf16": ([_p] * 9 + _DIMS8 + [_p, ctypes.c_size_t, _p], _i),
     "hipad_dfa_backward_stages": ([_i, _i] + [_p] * 9 + _DIMS8 + [_p, ctypes.c_size_t, _p], _i),
     "hipad_dfa_sample_indices": ([_p] * 4 + [_i] * 5 + [_p], _i),
     "hipad_dfa_fused_forward_f32": ([_p] * 9 + _DIMS8 + [_p], _i),

@@ -57,6 +57,7 @@ int backward_common(ElemType t, const void* feat, const int32_t* shapes, const i
     a.stage_mask = stage_mask & 7;
     a.separate_zero_fill = (stage_mask & 8) != 0;
     a.classify_only = (stage_mask & 16) != 0;
+    a.accumulate = (stage_mask & 32) != 0;
     return launch_backward(a);
 }
 }  // namespace
@@ -122,6 +123,32 @@ int hipad_dfa_backward_bf16(const uint16_t* mc_ms_feat, const int32_t* spatial_s
                            num_embeds, num_scale, num_anchors, num_pts, num_groups, workspace, workspace_bytes, stream);
 }
 
+int hipad_dfa_backward_accumulate_f32(const float* mc_ms_feat, const int32_t* spatial_shape,
+                                      const int32_t* scale_start_index, const float* sample_location,
+                                      const float* weights, const float* grad_output, float* grad_mc_ms_feat,
+                                      float* grad_sampling_location, float* grad_weights, int batch_size, int num_cams,
+                                      int num_feat, int num_embeds, int num_scale, int num_anchors, int num_pts,
+                                      int num_groups, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!grad_mc_ms_feat) return HIPAD_DFA_ERR_BAD_ARGUMENT;
+    return backward_common(kF32, mc_ms_feat, spatial_shape, scale_start_index, sample_location, weights, grad_output,
+                           grad_mc_ms_feat, grad_sampling_location, grad_weights, batch_size, num_cams, num_feat,
+                           num_embeds, num_scale, num_anchors, num_pts, num_groups, workspace, workspace_bytes, stream,
+                           7 | 32);
+}
+
+int hipad_dfa_backward_accumulate_bf16(const uint16_t* mc_ms_feat, const int32_t* spatial_shape,
+                                       const int32_t* scale_start_index, const float* sample_location,
+                                       const float* weights, const float* grad_output, uint16_t* grad_mc_ms_feat,
+                                       float* grad_sampling_location, float* grad_weights, int batch_size, int num_cams,
+                                       int num_feat, int num_embeds, int num_scale, int num_anchors, int num_pts,
+                                       int num_groups, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!grad_mc_ms_feat) return HIPAD_DFA_ERR_BAD_ARGUMENT;
+    return backward_common(kBF16, mc_ms_feat, spatial_shape, scale_start_index, sample_location, weights, grad_output,
+                           grad_mc_ms_feat, grad_sampling_location, grad_weights, batch_size, num_cams, num_feat,
+                           num_embeds, num_scale, num_anchors, num_pts, num_groups, workspace, workspace_bytes, stream,
+                           7 | 32);
+}
+
 int hipad_dfa_backward_stages(int feat_is_bf16, int stage_mask, const void* mc_ms_feat, const int32_t* spatial_shape,
                               const int32_t* scale_start_index, const float* sample_location, const float* weights,
                               const float* grad_output, void* grad_mc_ms_feat, float* grad_sampling_location,
@@ -131,7 +158,7 @@ int hipad_dfa_backward_stages(int feat_is_bf16, int stage_mask, const void* mc_m
     return backward_common(feat_is_bf16 ? kBF16 : kF32, mc_ms_feat, spatial_shape, scale_start_index, sample_location,
                            weights, grad_output, grad_mc_ms_feat, grad_sampling_location, grad_weights, batch_size,
                            num_cams, num_feat, num_embeds, num_scale, num_anchors, num_pts, num_groups, workspace,
-                           workspace_bytes, stream, stage_mask & 31);
+                           workspace_bytes, stream, stage_mask & 63);
 }
 
 int hipad_dfa_sample_indices(int32_t* indices, const int32_t* spatial_shape, const int32_t* scale_start_index,

@@ -119,7 +119,7 @@ int launch_backward(const BwdArgs& a) {
     if (smem > kSampleSmemBudget) return -2;
     const size_t gfeat_bytes = (size_t)d.bs * d.num_feat * d.C * (a.type == kF32 ? 4 : 2);
     if (a.stage_mask & 1) {
-        if (a.g_feat != nullptr) {
+        if (a.g_feat != nullptr && !a.accumulate) {
             const bool vec_ok = (gfeat_bytes % 16 == 0) && (reinterpret_cast<uintptr_t>(a.g_feat) % 16 == 0);
             if (vec_ok && grid >= 2 * 148 && !a.separate_zero_fill) {
                 p.zero_ptr = reinterpret_cast<uint4*>(a.g_feat);
@@ -168,6 +168,7 @@ int launch_backward(const BwdArgs& a) {
     const int buckets = d.cams * d.L * d.bs;
     int nb = (2 * 148) / buckets;
     gp.NB = nb < 1 ? 1 : (nb > kMaxBands ? kMaxBands : nb);
+    gp.accumulate = a.accumulate ? 1 : 0;
     gp.tiny_ok = (ks.vector && (d.C == 32 || d.C == 64 || d.C == 128 || d.C == 256) && (d.C / d.G) % 32 == 0 &&
                   hipad_env_int("HIPAD_DFA_TINY", 1) != 0) ? 1 : 0;
     if (a.stage_mask & 2) {

@@ -114,6 +114,11 @@ struct VecIO<__nv_bfloat16, 8> {
 
 template <>
 struct VecIO<__nv_bfloat16, 4> {   // 4 channels of a bf16 row (quarter-warp reduce)
+    static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&v)[4]) {
+        const uint2 t = *reinterpret_cast<const uint2*>(p);
+        v[0] = __uint_as_float(t.x << 16); v[1] = __uint_as_float(t.x & 0xffff0000u);
+        v[2] = __uint_as_float(t.y << 16); v[3] = __uint_as_float(t.y & 0xffff0000u);
+    }
     static __device__ __forceinline__ void store(__nv_bfloat16* p, const float (&v)[4]) {
         *reinterpret_cast<uint2*>(p) = make_uint2(float_to_bf16_bits(v[0]) | (float_to_bf16_bits(v[1]) << 16),
                                                   float_to_bf16_bits(v[2]) | (float_to_bf16_bits(v[3]) << 16));

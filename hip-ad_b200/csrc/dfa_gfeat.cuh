@@ -72,6 +72,7 @@ struct GfeatParams {
     int seg_stride;    // ints per batch element in seg
     int n_chunks;
     int NB;            // requested bands per bucket (<= kMaxBands)
+    int accumulate;    // add to the rows already in g_feat instead of overwriting them (shared buffer across calls)
     int tiny_ok;       // shape supported by the quarter-warp kernel (C % 32 == 0, C <= 256, (C/G) % 32 == 0)
 };
 
@@ -730,8 +731,16 @@ __global__ void __launch_bounds__(256, 2) dfa_gfeat_reduce_kernel(const GfeatPar
             if (write_row) {
                 T* dst = reinterpret_cast<T*>(p.g_feat) + (size_t)grow * d.C;
 #pragma unroll
-                for (int j = 0; j < NCH; ++j)
-                    if (lm.act[j]) VecIO<T, V>::store(dst + lm.ch[j], acc[j]);
+                for (int j = 0; j < NCH; ++j) {
+                    if (!lm.act[j]) continue;
+                    if (p.accumulate) {     // shared g_feat buffer: calls are serialised by the stream, so the order is fixed
+                        float old[V];
+                        VecIO<T, V>::load(dst + lm.ch[j], old);
+#pragma unroll
+                        for (int e = 0; e < V; ++e) acc[j][e] += old[e];
+                    }
+                    VecIO<T, V>::store(dst + lm.ch[j], acc[j]);
+                }
             }
         } else if constexpr (NQ > 0) {
             // ------------------------------------------------------------------ tiny item (4 rows)
@@ -806,7 +815,15 @@ __global__ void __launch_bounds__(256, 2) dfa_gfeat_reduce_kernel(const GfeatPar
             if (live) {
                 T* dst = reinterpret_cast<T*>(p.g_feat) + (size_t)grow * d.C + sub * 4;
 #pragma unroll
-                for (int i = 0; i < NQ1; ++i) VecIO<T, 4>::store(dst + i * 32, acc[i]);
+                for (int i = 0; i < NQ1; ++i) {
+                    if (p.accumulate) {
+                        float old[4];
+                        VecIO<T, 4>::load(dst + i * 32, old);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) acc[i][q] += old[q];
+                    }
+                    VecIO<T, 4>::store(dst + i * 32, acc[i]);
+                }
             }
         }
         cur = nxt;

@@ -57,6 +57,7 @@ struct BwdArgs {
     size_t workspace_bytes;
     cudaStream_t stream;
     int stage_mask;   // bit0 sample-major (g_w,g_loc) + zero fill of g_feat, bit1 compaction + band sort, bit2 reduce
+    bool accumulate;           // g_feat += (shared buffer across calls): no zero fill, touched rows are read-modify-written
     bool classify_only;        // debugging: stop after the row classification (stage bit 4 without the reduce)
     bool separate_zero_fill;   // measurement: never fold the zero fill into the sample-major kernel
 };

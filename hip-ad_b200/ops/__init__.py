@@ -14,6 +14,7 @@ from .deformable_aggregation import (  # noqa: F401
     format_feature_levels,
     fused_deformable_aggregation,
     sample_indices,
+    share_feature_gradient,
 )
 
 

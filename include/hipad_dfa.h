@@ -100,11 +100,36 @@ int hipad_dfa_backward_bf16(const uint16_t *mc_ms_feat,
                             int num_scale, int num_anchors, int num_pts, int num_groups,
                             void *workspace, size_t workspace_bytes, void *stream);
 
+/* Shared feature-gradient buffer ("next" row f1 of the scope table: one dense g_feat per decoder layer / per step
+ * instead of one per call).  Same as hipad_dfa_backward_*, except that grad_mc_ms_feat is NOT zero-filled and the
+ * touched rows are read-modify-written: grad_mc_ms_feat += this call's feature gradient.  The first call of a
+ * group uses hipad_dfa_backward_* (which writes every row), the others this one, all on one stream; the
+ * summation order is then the call order, i.e. still deterministic.  Removes the 115 MB zero fill per call and the
+ * caller's (autograd's) dense accumulation of one g_feat per call. */
+int hipad_dfa_backward_accumulate_f32(const float *mc_ms_feat,
+                                      const int32_t *spatial_shape, const int32_t *scale_start_index,
+                                      const float *sample_location, const float *weights,
+                                      const float *grad_output,
+                                      float *grad_mc_ms_feat, float *grad_sampling_location, float *grad_weights,
+                                      int batch_size, int num_cams, int num_feat, int num_embeds,
+                                      int num_scale, int num_anchors, int num_pts, int num_groups,
+                                      void *workspace, size_t workspace_bytes, void *stream);
+
+int hipad_dfa_backward_accumulate_bf16(const uint16_t *mc_ms_feat,
+                                       const int32_t *spatial_shape, const int32_t *scale_start_index,
+                                       const float *sample_location, const float *weights,
+                                       const float *grad_output,
+                                       uint16_t *grad_mc_ms_feat, float *grad_sampling_location, float *grad_weights,
+                                       int batch_size, int num_cams, int num_feat, int num_embeds,
+                                       int num_scale, int num_anchors, int num_pts, int num_groups,
+                                       void *workspace, size_t workspace_bytes, void *stream);
+
 /* Measurement variant of the backward: runs only the kernels selected by stage_mask
  * (bit0 = sample-major kernel writing grad_weights/grad_sampling_location, which also zero-fills
  * grad_mc_ms_feat; bit1 = visible-sample compaction + per-(b,cam,level,band) sort into the workspace;
  * bit2 = feature-major reduce overwriting the touched rows of grad_mc_ms_feat; 7 = the full backward;
- * bit3 = keep the zero fill in its own kernel instead of folding it into the sample-major kernel).
+ * bit3 = keep the zero fill in its own kernel instead of folding it into the sample-major kernel;
+ * bit5 = accumulate into grad_mc_ms_feat as hipad_dfa_backward_accumulate_* does).
  * bench.py uses it to put CUDA events around each stage; results are only meaningful when the stages
  * are issued in order on one stream with the same workspace. */
 int hipad_dfa_backward_stages(int feat_is_bf16, int stage_mask,

@@ -454,3 +454,60 @@ def test_format_feeds_the_op_end_to_end(ops, oracle_mod):
                                        case["grad_out"])
     got = torch.cat([f.grad.reshape(bs, cams, C, -1) for f in fmaps], dim=-1).permute(0, 1, 3, 2).flatten(1, 2)
     assert rel_err(got.cpu().numpy(), r_feat) <= FP32_TOL
+
+
+# ------------------------------------------------------------------------------------- shared feature-gradient buffer
+@pytest.mark.parametrize("bf16", [False, True])
+def test_shared_feature_gradient_matches_per_call_gradients(ops, bf16):
+    """Three aggregation calls on one feature tensor: with share_feature_gradient() their feature gradients are
+    accumulated in ONE buffer by the kernels (hipad_dfa_backward_accumulate_*); the result must equal autograd's sum of
+    the three per-call dense gradients, and the other gradients must be bit-identical."""
+    names = ["c256_g8_l4", "map_like_slices", "plan_like_slices"]
+    cases = [small_case(n, seed=20 + i) for i, n in enumerate(names)]
+    base = cases[0]
+    cases[1] = H.make_case(21, 2, 6, [(16, 28), (8, 14), (4, 7), (2, 4)], 256, 8, 10, 300)   # same bs / feature geometry
+    cases[2] = H.make_case(22, 2, 6, [(16, 28), (8, 14), (4, 7), (2, 4)], 256, 8, 48, 90)
+    dt = torch.bfloat16 if bf16 else None
+
+    def run(shared):
+        feat = dev(base["feat"], dt).requires_grad_(True)
+        f = ops.share_feature_gradient(feat) if shared else feat
+        leaves, outs = [], []
+        for c in cases:
+            loc, w = dev(c["loc"]).requires_grad_(True), dev(c["weights"]).requires_grad_(True)
+            outs.append(ops.deformable_aggregation_function(f, dev(base["shapes"]).long(), dev(base["starts"]).long(), loc, w))
+            leaves.append((loc, w))
+        extra = (f.float() * 0.5).sum()                      # a consumer that is not an aggregation call
+        torch.autograd.backward(outs + [extra], [dev(c["grad_out"]) for c in cases] + [torch.ones((), device="cuda")])
+        torch.cuda.synchronize()
+        return feat.grad.float().cpu().numpy(), [(l.grad.cpu().numpy(), w.grad.cpu().numpy()) for l, w in leaves]
+
+    g_ref, leaves_ref = run(False)
+    g_sh, leaves_sh = run(True)
+    assert rel_err(g_sh, g_ref) <= (BF16_TOL if bf16 else FP32_TOL)
+    for (l0, w0), (l1, w1) in zip(leaves_ref, leaves_sh):
+        assert np.array_equal(l0, l1) and np.array_equal(w0, w1)
+    g_sh2, _ = run(True)
+    assert np.array_equal(g_sh, g_sh2)                       # deterministic
+
+
+def test_backward_accumulate_abi_adds_to_the_buffer(ops, cuda_lib, oracle_mod):
+    case = small_case("c256_g8_l4", seed=31)
+    feat, loc, w, go = dev(case["feat"]), dev(case["loc"]), dev(case["weights"]), dev(case["grad_out"])
+    sh, st = dev(case["shapes"]).int(), dev(case["starts"]).int()
+    bs, F, C = feat.shape
+    A, P, cams = loc.shape[1:4]
+    dims = (bs, cams, F, C, sh.shape[1], A, P, w.shape[-1])
+    nb = cuda_lib.hipad_dfa_backward_workspace_bytes(*dims)
+    ws = torch.empty(nb, dtype=torch.uint8, device="cuda")
+    g_feat = torch.full_like(feat, 0.25)
+    g_loc, g_w = torch.empty_like(loc), torch.empty_like(w)
+    rc = cuda_lib.hipad_dfa_backward_accumulate_f32(feat.data_ptr(), sh.data_ptr(), st.data_ptr(), loc.data_ptr(), w.data_ptr(),
+                                                    go.data_ptr(), g_feat.data_ptr(), g_loc.data_ptr(), g_w.data_ptr(), *dims,
+                                                    ws.data_ptr(), nb, torch.cuda.current_stream().cuda_stream)
+    assert rc == 0
+    torch.cuda.synchronize()
+    r_feat, r_loc, r_w = oracle_mod.backward(case["feat"], case["shapes"], case["starts"], case["loc"], case["weights"],
+                                             case["grad_out"])
+    assert rel_err(g_feat.cpu().numpy(), r_feat + 0.25) <= FP32_TOL
+    assert rel_err(g_loc.cpu().numpy(), r_loc) <= FP32_TOL and rel_err(g_w.cpu().numpy(), r_w) <= FP32_TOL
