@@ -109,7 +109,7 @@ int launch_backward(const BwdArgs& a) {
     p.d = d;
     const int NP = d.P * d.cams;
     const long long rows = (long long)d.bs * d.A;
-    p.S = choose_slices(rows, NP, 4 * 148, sample_smem_per_pair(kBwd, d.L), /*max_slices=*/1 << 20);
+    p.S = choose_slices(rows, NP, 8 * 148, sample_smem_per_pair(kBwd, d.L), /*max_slices=*/1 << 20);
     if (p.S == 0 || d.bs > 65535 || (long long)d.bs * d.num_feat >= (1LL << 31)) return -2;
     p.PS = (NP + p.S - 1) / p.S;
     const long long grid = rows * p.S;

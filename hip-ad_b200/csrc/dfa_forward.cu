@@ -24,10 +24,18 @@ KernelShape pick_shape(ElemType t, int C, int G, bool aligned16) {
 }
 
 int choose_slices(long long rows, int pairs, int target_ctas, int bytes_per_pair, int max_slices) {
+    // Measured on B200 (gpurun r01n-r01p, stage-2 shapes):
+    //  * forward (max_slices = 8, the slices of a row are a thread-block cluster): cluster gang scheduling costs
+    //    ~25 us per launch, so rows are sliced only when there are fewer rows than CTA slots (2 per SM);
+    //  * backward (no cluster, nothing to combine across slices): ~8 CTAs per SM worth of slices while a slice keeps
+    //    >= 48 (p,cam) pairs (map: S=16 81.9 us vs S=8 95.1; plan: S=4 85.0 vs S=2 89.1; det stays S=1).
+    const bool clustered = max_slices <= 8;
+    const int min_pairs = clustered ? 64 : 48;
     int S = 1;
-    while (S < 8 && S * 2 <= max_slices && rows * S < target_ctas && pairs / (S * 2) >= 64) S *= 2;
+    if (!clustered || rows < 2 * 148)
+        while (S < 64 && S * 2 <= max_slices && rows * S < target_ctas && pairs / (S * 2) >= min_pairs) S *= 2;
     const int forced = hipad_env_int("HIPAD_DFA_SLICES", 0);   // A/B knob
-    if (forced > 0 && forced <= max_slices && forced <= 8) S = forced;
+    if (forced > 0 && forced <= max_slices && forced <= 64) S = forced;
     // fixed part of the CTA's shared memory (tables, reduction scratch) is < 48 KB for every supported shape
     const long long budget = (long long)kSampleSmemBudget - 48 * 1024;
     while ((long long)((pairs + S - 1) / S) * bytes_per_pair > budget) {
