@@ -511,3 +511,70 @@ def test_backward_accumulate_abi_adds_to_the_buffer(ops, cuda_lib, oracle_mod):
                                              case["grad_out"])
     assert rel_err(g_feat.cpu().numpy(), r_feat + 0.25) <= FP32_TOL
     assert rel_err(g_loc.cpu().numpy(), r_loc) <= FP32_TOL and rel_err(g_w.cpu().numpy(), r_w) <= FP32_TOL
+
+
+# ------------------------------------------------------------------------------------- the other BASELINE.json configs
+def _check_vs_oracle(ops, oracle_mod, case, bf16=False):
+    out, g_feat, g_loc, g_w = run_bwd(ops, case, bf16=bf16)
+    feat = case["feat"]
+    if bf16:   # the oracle sees the same rounded feature values the kernel reads
+        feat = torch.as_tensor(feat).bfloat16().float().numpy()
+    ref = oracle_mod.forward(feat, case["shapes"], case["starts"], case["loc"], case["weights"])
+    r_feat, r_loc, r_w = oracle_mod.backward(feat, case["shapes"], case["starts"], case["loc"], case["weights"],
+                                             case["grad_out"])
+    tol = BF16_TOL if bf16 else FP32_TOL
+    assert rel_err(out, ref) <= FP32_TOL          # forward accumulates in fp32 either way
+    assert rel_err(g_feat, r_feat) <= tol         # bf16: the gradient is stored as bf16
+    assert rel_err(g_loc, r_loc) <= FP32_TOL and rel_err(g_w, r_w) <= FP32_TOL
+
+
+def test_config0_256x704_det_vs_oracle(ops, oracle_mod):
+    """BASELINE.json configs[0]: bs=1, 6 cams, 4 levels of a 256x704 input, 900 det anchors x 13 key points, 8 groups."""
+    _check_vs_oracle(ops, oracle_mod, H.make_geo_case(40, "det", 1, H.LEVELS_256x704, (256, 704)))
+
+
+def test_config4_hires_512x1408_vs_oracle_and_indices(ops, oracle_mod):
+    """BASELINE.json configs[4]: 512x1408 input (F = 359 040 rows, 368 MB of fp32 features per sample)."""
+    case = H.make_geo_case(41, "det", 1, H.LEVELS_512x1408, (512, 1408))
+    _check_vs_oracle(ops, oracle_mod, case)
+    idx = ops.sample_indices(dev(case["shapes"]).long(), dev(case["starts"]).long(), dev(case["loc"])).cpu().numpy()
+    assert np.array_equal(idx, oracle_mod.indices(case["shapes"], case["starts"], case["loc"]))
+
+
+@pytest.mark.parametrize("A,P,bf16", [(1800, 20, False), (2700, 7, True), (3600, 32, False)])
+def test_config3_sweep_points(ops, oracle_mod, A, P, bf16):
+    """BASELINE.json configs[3] (anchors 900-3600, key points 7-32, bf16 / fp32): mid-size points against the oracle,
+    the largest one (A*P = 115 200 samples per camera) through size-independent properties."""
+    case = H.make_geo_case(42 + A, "det", 1, H.LEVELS_352x640, (352, 640), A=A, P=P)
+    if A * P <= 40000:
+        _check_vs_oracle(ops, oracle_mod, case, bf16=bf16)
+        return
+    out1, g_feat1, g_loc1, g_w1 = run_bwd(ops, case, bf16=bf16)
+    out2, g_feat2, g_loc2, g_w2 = run_bwd(ops, case, bf16=bf16)
+    for a, b in ((out1, out2), (g_feat1, g_feat2), (g_loc1, g_loc2), (g_w1, g_w2)):
+        assert np.array_equal(a, b), "results must be bitwise reproducible"
+    lhs = float((case["grad_out"].astype(np.float64) * out1).sum())
+    assert abs(float((g_w1.astype(np.float64) * case["weights"]).sum()) - lhs) <= 1e-4 * max(1.0, abs(lhs))
+    assert abs(float((g_feat1.astype(np.float64) * case["feat"]).sum()) - lhs) <= 1e-4 * max(1.0, abs(lhs))
+    # and a random subset of output rows against the oracle
+    sel = np.random.default_rng(0).choice(A, 64, replace=False)
+    sub = dict(case, loc=case["loc"][:, sel], weights=case["weights"][:, sel], grad_out=case["grad_out"][:, sel])
+    assert rel_err(out1[:, sel], oracle_mod.forward(sub["feat"], sub["shapes"], sub["starts"], sub["loc"], sub["weights"])) <= FP32_TOL
+
+
+def test_pile_up_on_one_pixel_goes_through_many_parts(ops, oracle_mod):
+    """Every sample of every anchor hits the same few pixels: feature rows with thousands of contributions are split
+    into 32-contribution parts whose partial sums are combined in part order (dfa_gfeat_reduce_kernel)."""
+    case = small_case("c256_g8_l4", seed=50)
+    bs, A, P, cams, _ = case["loc"].shape
+    rng = np.random.default_rng(5)
+    case["loc"] = (0.5 + 0.01 * rng.standard_normal(case["loc"].shape)).astype(np.float32)   # all visible, same spot
+    _check_vs_oracle(ops, oracle_mod, case)
+    out1 = run_bwd(ops, case)
+    out2 = run_bwd(ops, case)
+    assert all(np.array_equal(a, b) for a, b in zip(out1, out2))
+
+
+def test_batch_of_eight(ops, oracle_mod):
+    case = H.make_case(60, 8, 6, [(16, 28), (8, 14), (4, 7), (2, 4)], 256, 8, 23, 13)
+    _check_vs_oracle(ops, oracle_mod, case)
