@@ -125,7 +125,7 @@ int launch_backward(const BwdArgs& a) {
                 p.zero_ptr = reinterpret_cast<uint4*>(a.g_feat);
                 p.zero_n16 = (long long)(gfeat_bytes / 16);
             } else if (vec_ok) {
-                dfa_zero_kernel<<<148 * 8, 256, 0, a.stream>>>(reinterpret_cast<uint4*>(a.g_feat),
+                dfa_zero_kernel<<<148 * 16, 256, 0, a.stream>>>(reinterpret_cast<uint4*>(a.g_feat),
                                                               (long long)(gfeat_bytes / 16));
                 const cudaError_t e = cudaGetLastError();
                 if (e != cudaSuccess) return (int)e;
@@ -159,6 +159,10 @@ int launch_backward(const BwdArgs& a) {
     gp.partial = reinterpret_cast<float*>(ws + wl.partial);
     gp.unit_done = reinterpret_cast<int*>(ws + wl.unit_done);
     gp.partial_cap = (int)wl.partial_slots;
+    {   // test knob: shrink the partial-slot pool to exercise the single-warp fallback of rows that find no slots
+        const int cap = hipad_env_int("HIPAD_DFA_PARTIAL_CAP", -1);
+        if (cap >= 0 && cap < gp.partial_cap) gp.partial_cap = cap;
+    }
     gp.tiny_list = reinterpret_cast<int4*>(ws + wl.tiny_list);
     gp.counters = reinterpret_cast<int*>(ws + wl.counters);
     gp.d = d;

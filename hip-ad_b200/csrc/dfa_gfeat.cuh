@@ -103,7 +103,14 @@ __device__ __forceinline__ size_t seg_offset(int start) { return (size_t)kSegSca
 __global__ void __launch_bounds__(256) dfa_zero_kernel(uint4* __restrict__ dst, long long n16) {
     const long long stride = (long long)gridDim.x * blockDim.x;
     const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) dst[i] = z;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + 3 * stride < n16; i += 4 * stride) {     // four independent 16-byte stores per thread and trip
+        dst[i] = z;
+        dst[i + stride] = z;
+        dst[i + 2 * stride] = z;
+        dst[i + 3 * stride] = z;
+    }
+    for (; i < n16; i += stride) dst[i] = z;
 }
 
 // ------------------------------------------------------------------------------------------ compaction
@@ -376,7 +383,17 @@ __global__ void __launch_bounds__(kSortThreads) dfa_band_sort_kernel(const Gfeat
         const int* bcnt = p.band_cnt + ((size_t)b_idx * d.cams + cam) * p.n_chunks * d.L * kMaxBands + l * kMaxBands + band;
         for (int c = tid; c < p.n_chunks; c += kSortThreads) s_coff[c] = __ldg(bcnt + (size_t)c * d.L * kMaxBands);
     }
+    if (warp == 1) {    // visible samples of the whole camera: nothing to do for any band when there are none
+        const int* cnts = p.vis_cnt + ((size_t)b_idx * d.cams + cam) * p.n_chunks;
+        int t = 0;
+        for (int c = lane; c < p.n_chunks; c += 32) t += __ldg(cnts + c);
+        t = __reduce_add_sync(0xffffffffu, t);
+        if (lane == 0) s_misc[2] = t;
+    }
     __syncthreads();
+    // A camera that sees no sample at all (rear cameras of the planning query, every camera of the ego query):
+    // its buckets stay empty (cursor == 0), which the row classification checks before it reads any segment table
+    if (s_misc[2] == 0) return;
     if (warp == 0) {    // exclusive scan over the chunks
         int run = 0;
         for (int c0 = 0; c0 < p.n_chunks; c0 += 32) {
@@ -576,7 +593,8 @@ __global__ void __launch_bounds__(kClassifyThreads) dfa_row_classify_kernel(cons
             const int h = s_tab[cl * 3], w = s_tab[cl * 3 + 1], st = s_tab[cl * 3 + 2];
             const Bands g = band_geometry(h, w, p.NB);
             const int r = row - st, y = r / w, x = r - y * w;
-            n = row_segments(p.seg + (size_t)b_idx * p.seg_stride + seg_offset(st), g, y, x, beg, e1, e2, e3);
+            if (__ldg(p.cursor + (size_t)b_idx * n_cl + cl) > 0)     // empty bucket: its tables were never written
+                n = row_segments(p.seg + (size_t)b_idx * p.seg_stride + seg_offset(st), g, y, x, beg, e1, e2, e3);
         }
     }
     const bool tiny = p.tiny_ok && n > 0 && n <= kTinyRow;

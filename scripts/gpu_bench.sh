@@ -17,4 +17,4 @@ for f in ("bench_f32","bench_f32_serial","bench_bf16","bench_f32_bs4"):
         d=json.load(open("$OUT/%s.json"%f)); print(f, "value", d["value"], "ms", d["ms_per_step"], "e2e", d["e2e"] and d["e2e"]["value"], "roofline", d["roofline"]["kernel"], d["roofline"]["frac"], d["kernel_avg_us"])
     except Exception as e: print(f, "failed", e)
 PY
-tail -3 $OUT/*.err
+for f in $OUT/*.err; do tail -2 $f; done

@@ -578,3 +578,17 @@ def test_pile_up_on_one_pixel_goes_through_many_parts(ops, oracle_mod):
 def test_batch_of_eight(ops, oracle_mod):
     case = H.make_case(60, 8, 6, [(16, 28), (8, 14), (4, 7), (2, 4)], 256, 8, 23, 13)
     _check_vs_oracle(ops, oracle_mod, case)
+
+
+def test_partial_slot_exhaustion_falls_back_to_single_warp_rows(ops, oracle_mod, monkeypatch):
+    """Rows with more than 32 contributions normally go through partial-sum slots; when the pool is exhausted
+    (forced here with HIPAD_DFA_PARTIAL_CAP) such a row is summed by one warp instead, with the same result."""
+    case = small_case("c256_g8_l4", seed=51)
+    case["loc"] = (0.5 + 0.02 * np.random.default_rng(6).standard_normal(case["loc"].shape)).astype(np.float32)
+    ref = run_bwd(ops, case)
+    monkeypatch.setenv("HIPAD_DFA_PARTIAL_CAP", "5")
+    got = run_bwd(ops, case)
+    monkeypatch.delenv("HIPAD_DFA_PARTIAL_CAP")
+    _check_vs_oracle(ops, oracle_mod, case)
+    for a, b in zip(ref, got):     # a different summation split for the overflowing rows: equal to fp32 accuracy
+        assert rel_err(b, a) <= FP32_TOL
