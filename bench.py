@@ -61,7 +61,9 @@ def make_calls(bs, seed, layers=LAYERS, modalities=MODALITIES):
                     c["loc"].shape, dtype=np.float32)
             rng = np.random.default_rng(seed * 77 + layer * 10 + mi)
             calls.append(dict(kind=kind, layer=layer, A=A, P=P, loc=c["loc"], weights=c["weights"],
-                              grad_out=rng.standard_normal((bs, A, C), dtype=np.float32)))
+                              grad_out=rng.standard_normal((bs, A, C), dtype=np.float32),
+                              key_points=c["key_points"].astype(np.float32), logits=c["logits"],
+                              projection_mat=c["projection_mat"].astype(np.float32), image_wh=c["image_wh"]))
     import helpers
     shapes, starts, F = helpers.level_tables(level_hw(FINAL_HW), CAMS)
     return calls, shapes, starts, F
@@ -334,6 +336,46 @@ def gpu_arm(args):
     ms_per_step = total_ms / args.steps
     value = whole_job_gbs(world, step_bytes, ms_per_step)
 
+    # ---- BASELINE configs[1]: decoder FORWARD at bs-per-GPU inference, every DFA call through the fused kernel
+    # (key-point projection + group softmax + aggregation in one launch, raw weights_fc logits in)
+    inference = None
+    if not args.no_graph:
+        try:
+            fused_fn = lib.hipad_dfa_fused_forward_bf16 if bf16 else lib.hipad_dfa_fused_forward_f32
+            for c in calls:
+                c["kp_d"] = torch.from_numpy(np.ascontiguousarray(c["key_points"])).to(dev)
+                c["lg_d"] = torch.from_numpy(np.ascontiguousarray(c["logits"])).to(dev)
+                c["pm_d"] = torch.from_numpy(np.ascontiguousarray(c["projection_mat"])).to(dev)
+                c["wh_d"] = torch.from_numpy(np.ascontiguousarray(c["image_wh"])).to(dev)
+
+            def fused_call(c, s_):
+                _lib.check(fused_fn(c["out_d"].data_ptr(), feat.data_ptr(), shapes_d.data_ptr(), starts_d.data_ptr(),
+                                    c["kp_d"].data_ptr(), c["pm_d"].data_ptr(), c["wh_d"].data_ptr(), c["lg_d"].data_ptr(),
+                                    None, *dims(c), s_), "fused forward")
+
+            def issue_inference(main):
+                for group in layers:
+                    layer_group(group, fused_call, main)
+
+            with torch.cuda.stream(stream):
+                issue_inference(stream)
+                torch.cuda.synchronize()
+                g3 = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g3, stream=stream):
+                    issue_inference(torch.cuda.current_stream())
+                for _ in range(3):
+                    flush_l2(); g3.replay()
+                ev3 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+                for a, b in ev3:
+                    flush_l2(); a.record(); g3.replay(); b.record()
+                torch.cuda.synchronize()
+            ms3 = max_over_ranks(float(sum(a.elapsed_time(b) for a, b in ev3)), dev) / args.steps
+            inference = {"ms_per_forward": round(ms3, 4), "samples_per_s": round(world * bs / (ms3 * 1e-3), 1),
+                         "note": "24 fused DFA calls of one stage-2 decoder forward (projection + softmax + aggregation "
+                                 "per launch), one CUDA graph, L2 flushed between replays"}
+        except Exception as e:
+            inference = {"error": str(e)[:200]}
+
     # ---- same step with one shared g_feat buffer (reported beside the headline, never instead of it)
     shared = None
     if not args.no_graph:
@@ -528,7 +570,7 @@ def gpu_arm(args):
             "samples_per_s": round(world * bs / (ms_per_step * 1e-3), 2),
             "algorithmic_bytes_per_step": int(step_bytes),
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
-            "roofline": roofline, "cpu_baseline": cpu_baseline, "shared_gfeat_step": shared,
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "shared_gfeat_step": shared, "decoder_forward_inference": inference,
             "per_call_us": {k: {"fwd": round(float(np.mean(v["fwd_us"])), 1), "bwd": round(float(np.mean(v["bwd_us"])), 1),
                                 "B_fwd": v["bytes"]["fwd"], "B_bwd": v["bytes"]["bwd"], "U_rows": v["bytes"]["U"]}
                             for k, v in per_mod.items()},

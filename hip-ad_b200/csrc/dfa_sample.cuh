@@ -229,23 +229,53 @@ __global__ void __launch_bounds__(kWarps * 32) dfa_sample_kernel(const SamplePar
         chunk = (chunk + kThreads - 1) / kThreads * kThreads;   // keeps (idx % G) fixed per thread
         const int lo = min(n_log, slice * chunk), hi = min(n_log, lo + chunk);
         float m_run = -INFINITY, s_run = 0.f;
-        for (int i = lo + tid; i < hi; i += kThreads) {
-            const float x = __ldg(lg_row + i);
-            if (x > m_run) {
-                s_run = s_run * expf(m_run - x) + 1.f;
-                m_run = x;
-            } else {
-                s_run += expf(x - m_run);
+        for (int i0 = lo + tid; i0 < hi; i0 += kThreads * 8) {
+            // eight independent loads in flight per thread, then one max and one rescale for the batch
+            float x[8];
+            float mx = m_run;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int i = i0 + u * kThreads;
+                x[u] = (i < hi) ? __ldg(lg_row + i) : -INFINITY;
             }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) mx = fmaxf(mx, x[u]);
+            float acc = (s_run == 0.f) ? 0.f : s_run * expf(m_run - mx);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) acc += expf(x[u] - mx);     // exp(-inf) = 0 for the padding
+            m_run = mx;
+            s_run = acc;
         }
-        s_red2[tid * 2] = m_run;
-        s_red2[tid * 2 + 1] = s_run;
+        // combine the per-thread (max, sum) pairs of each group: thread t saw group (lo + t) % G = t % G (lo is a
+        // multiple of kThreads, kThreads % G == 0).  When G divides 32 the lanes of a warp that share a group are
+        // merged with shuffles first, so the final per-group loop runs over kWarps entries instead of kThreads.
+        const bool g_pow2 = (d.G & (d.G - 1)) == 0 && d.G <= 32;
+        if (g_pow2) {
+            for (int o = 16; o >= d.G; o >>= 1) {
+                const float mo = __shfl_xor_sync(0xffffffffu, m_run, o), so_ = __shfl_xor_sync(0xffffffffu, s_run, o);
+                const float mn = fmaxf(m_run, mo);
+                const float a_ = (s_run == 0.f) ? 0.f : s_run * expf(m_run - mn);
+                const float b_ = (so_ == 0.f) ? 0.f : so_ * expf(mo - mn);
+                m_run = mn;
+                s_run = a_ + b_;
+            }
+            if (lane < d.G) {
+                s_red2[(warp * d.G + lane) * 2] = m_run;
+                s_red2[(warp * d.G + lane) * 2 + 1] = s_run;
+            }
+        } else {
+            s_red2[tid * 2] = m_run;
+            s_red2[tid * 2 + 1] = s_run;
+        }
         __syncthreads();
-        if (tid < d.G) {   // kThreads % G == 0 (checked on the host): thread t saw group (lo+t) % G
+        if (tid < d.G) {
             float m = -INFINITY, s = 0.f;
-            for (int t = 0; t < kThreads; ++t) {
-                if ((lo + t) % d.G != tid) continue;
-                const float mt = s_red2[t * 2], st = s_red2[t * 2 + 1];
+            const int n_ent = g_pow2 ? kWarps : kThreads;
+            for (int t = 0; t < n_ent; ++t) {
+                int at = t;
+                if (g_pow2) at = t * d.G + tid;
+                else if (t % d.G != tid) continue;
+                const float mt = s_red2[at * 2], st = s_red2[at * 2 + 1];
                 if (st == 0.f) continue;
                 const float mn = fmaxf(m, mt);
                 s = s * expf(m - mn) + st * expf(mt - mn);
