@@ -739,13 +739,36 @@ __global__ void __launch_bounds__(256, 2) dfa_gfeat_reduce_kernel(const GfeatPar
                     for (int j = 0; j < NCH; ++j)
 #pragma unroll
                         for (int e = 0; e < V; ++e) acc[j][e] = 0.f;
-                    for (int uu = 0; uu < parts; ++uu) {
-                        const float* part = p.partial + (size_t)(slot + uu) * d.C;
+                    // eight part rows in flight at a time (vector loads that bypass L1), added in part order
+                    for (int u0 = 0; u0 < parts; u0 += 8) {
+                        float4 t[8][NCH];
 #pragma unroll
-                        for (int j = 0; j < NCH; ++j) {
-                            if (!lm.act[j]) continue;
+                        for (int k = 0; k < 8; ++k) {
+                            const float* part = p.partial + (size_t)(slot + min(u0 + k, parts - 1)) * d.C;
 #pragma unroll
-                            for (int e = 0; e < V; ++e) acc[j][e] += __ldcg(part + lm.ch[j] + e);
+                            for (int j = 0; j < NCH; ++j) {
+                                if constexpr (V == 4) {
+                                    t[k][j] = __ldcg(reinterpret_cast<const float4*>(part + lm.ch[j]));
+                                } else {
+                                    t[k][j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                                }
+                            }
+                        }
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) {
+                            if (u0 + k >= parts) break;      // warp-uniform
+                            const float* part = p.partial + (size_t)(slot + u0 + k) * d.C;
+#pragma unroll
+                            for (int j = 0; j < NCH; ++j) {
+                                if (!lm.act[j]) continue;
+                                if constexpr (V == 4) {
+                                    acc[j][0] += t[k][j].x; acc[j][1] += t[k][j].y;
+                                    acc[j][2] += t[k][j].z; acc[j][3] += t[k][j].w;
+                                } else {
+#pragma unroll
+                                    for (int e = 0; e < V; ++e) acc[j][e] += __ldcg(part + lm.ch[j] + e);
+                                }
+                            }
                         }
                     }
                 }
