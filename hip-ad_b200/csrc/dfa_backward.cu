@@ -68,6 +68,15 @@ int launch_reduce_nq(const GfeatParams& gp, cudaStream_t st) {
 template <typename T>
 int launch_reduce(const GfeatParams& gp, KernelShape ks, cudaStream_t st) {
     constexpr int VV = 16 / (int)sizeof(T);
+    if (ks.vector && sizeof(T) == 2) {
+        // grad_out and the partial sums are fp32 whatever the feature type: use the fp32 lane map (4 channels per lane,
+        // 512 contiguous bytes per warp load) and store 4 bf16 per lane; the 8-channel map reads half of every sector
+        const int C = gp.d.C;
+        if (C <= 128) return launch_reduce_nq<T, 4, 1>(gp, st);
+        if (C == 256) return launch_reduce_nq<T, 4, 2>(gp, st);
+        if (C == 384) return launch_reduce_nq<T, 4, 3>(gp, st);
+        if (C == 512) return launch_reduce_nq<T, 4, 4>(gp, st);
+    }
     if (ks.vector) {
         if (ks.nch == 1) return launch_reduce_nq<T, VV, 1>(gp, st);
         if (ks.nch == 2) return launch_reduce_nq<T, VV, 2>(gp, st);

@@ -135,6 +135,24 @@ struct VecIO<__nv_bfloat16, 1> {
     }
 };
 
+// 16-byte read-only load whose position in the instruction stream is pinned (asm volatile): the software pipeline
+// of the packed-bf16 gather depends on the loads of item q+3 being ISSUED before item q is consumed, and nvcc
+// otherwise sinks plain __ldg loads next to their first use.
+__device__ __forceinline__ uint4 ldg_nc_v4_pinned(const void* p) {
+    uint4 t;
+    asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(t.x), "=r"(t.y), "=r"(t.z), "=r"(t.w) : "l"(p));
+    return t;
+}
+
+__device__ __forceinline__ void unpack_bf16x8(const uint4& t, float (&v)[8]) {
+    const uint32_t u[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        v[2 * i] = __uint_as_float(u[i] << 16);
+        v[2 * i + 1] = __uint_as_float(u[i] & 0xffff0000u);
+    }
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -740,19 +740,22 @@ __global__ void __launch_bounds__(256, 2) dfa_gfeat_reduce_kernel(const GfeatPar
 #pragma unroll
                         for (int e = 0; e < V; ++e) acc[j][e] = 0.f;
                     // eight part rows in flight at a time (vector loads that bypass L1), added in part order
+                    constexpr int kQ = (V % 4 == 0) ? V / 4 : 1;      // float4 pieces of this lane's V channels
                     for (int u0 = 0; u0 < parts; u0 += 8) {
-                        float4 t[8][NCH];
+                        float4 t[8][NCH][kQ];
 #pragma unroll
                         for (int k = 0; k < 8; ++k) {
                             const float* part = p.partial + (size_t)(slot + min(u0 + k, parts - 1)) * d.C;
 #pragma unroll
-                            for (int j = 0; j < NCH; ++j) {
-                                if constexpr (V == 4) {
-                                    t[k][j] = __ldcg(reinterpret_cast<const float4*>(part + lm.ch[j]));
-                                } else {
-                                    t[k][j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                            for (int j = 0; j < NCH; ++j)
+#pragma unroll
+                                for (int q = 0; q < kQ; ++q) {
+                                    if constexpr (V % 4 == 0) {
+                                        t[k][j][q] = __ldcg(reinterpret_cast<const float4*>(part + lm.ch[j]) + q);
+                                    } else {
+                                        t[k][j][q] = make_float4(0.f, 0.f, 0.f, 0.f);
+                                    }
                                 }
-                            }
                         }
 #pragma unroll
                         for (int k = 0; k < 8; ++k) {
@@ -761,9 +764,12 @@ __global__ void __launch_bounds__(256, 2) dfa_gfeat_reduce_kernel(const GfeatPar
 #pragma unroll
                             for (int j = 0; j < NCH; ++j) {
                                 if (!lm.act[j]) continue;
-                                if constexpr (V == 4) {
-                                    acc[j][0] += t[k][j].x; acc[j][1] += t[k][j].y;
-                                    acc[j][2] += t[k][j].z; acc[j][3] += t[k][j].w;
+                                if constexpr (V % 4 == 0) {
+#pragma unroll
+                                    for (int q = 0; q < kQ; ++q) {
+                                        acc[j][4 * q + 0] += t[k][j][q].x; acc[j][4 * q + 1] += t[k][j][q].y;
+                                        acc[j][4 * q + 2] += t[k][j][q].z; acc[j][4 * q + 3] += t[k][j][q].w;
+                                    }
                                 } else {
 #pragma unroll
                                     for (int e = 0; e < V; ++e) acc[j][e] += __ldcg(part + lm.ch[j] + e);

@@ -391,8 +391,12 @@ __global__ void __launch_bounds__(kWarps * 32) dfa_sample_kernel(const SamplePar
     const int n_items = n_list * L;
     constexpr bool kConstChunks = (V > 1);   // vector path: full chunks (host guarantees it when NCH > 1)
 
+    // bf16 x8 rows at one chunk per lane stay PACKED (4 registers per corner) while in flight, which lets the gather
+    // run 4 items deep in the registers the fp32 path needs for 2; every other instantiation is unchanged
+    constexpr bool kPacked = (sizeof(T) == 2 && V == 8 && NCH == 1);
     struct Item {
-        float v[4][NCH][V];
+        float v[4][kPacked ? 1 : NCH][kPacked ? 1 : V];
+        uint4 raw[kPacked ? 4 : 1];
         float wv[NCH];
         float4 cf;
         int woff;
@@ -418,10 +422,17 @@ __global__ void __launch_bounds__(kWarps * 32) dfa_sample_kernel(const SamplePar
         for (int j = 0; j < NCH; ++j) {
             const int dj = kConstChunks ? j * 32 * V : ch[j] - ch[0];          // channels
             r.wv[j] = __ldg(wp + (grp[j] - grp[0]));
-            VecIO<T, V>::load(reinterpret_cast<const T*>(q1) + dj, r.v[0][j]);
-            VecIO<T, V>::load(reinterpret_cast<const T*>(q2) + dj, r.v[1][j]);
-            VecIO<T, V>::load(reinterpret_cast<const T*>(q3) + dj, r.v[2][j]);
-            VecIO<T, V>::load(reinterpret_cast<const T*>(q4) + dj, r.v[3][j]);
+            if constexpr (kPacked) {
+                r.raw[0] = ldg_nc_v4_pinned(reinterpret_cast<const T*>(q1) + dj);
+                r.raw[1] = ldg_nc_v4_pinned(reinterpret_cast<const T*>(q2) + dj);
+                r.raw[2] = ldg_nc_v4_pinned(reinterpret_cast<const T*>(q3) + dj);
+                r.raw[3] = ldg_nc_v4_pinned(reinterpret_cast<const T*>(q4) + dj);
+            } else {
+                VecIO<T, V>::load(reinterpret_cast<const T*>(q1) + dj, r.v[0][j]);
+                VecIO<T, V>::load(reinterpret_cast<const T*>(q2) + dj, r.v[1][j]);
+                VecIO<T, V>::load(reinterpret_cast<const T*>(q3) + dj, r.v[2][j]);
+                VecIO<T, V>::load(reinterpret_cast<const T*>(q4) + dj, r.v[3][j]);
+            }
         }
     };
 
@@ -433,6 +444,16 @@ __global__ void __launch_bounds__(kWarps * 32) dfa_sample_kernel(const SamplePar
         if (kMode != kBwd) {
 #pragma unroll
             for (int j = 0; j < NCH; ++j) {
+                float vv[4][V];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    if constexpr (kPacked) {
+                        unpack_bf16x8(r.raw[k], vv[k]);
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < V; ++e) vv[k][e] = r.v[k][j][e];
+                    }
+                }
                 float wj = r.wv[j];
                 if (kMode == kFused) wj = expf(wj - sm_m[j]) * sm_inv[j];
                 // weight folded into the four bilinear coefficients: 4 FMAs per channel,
@@ -444,7 +465,7 @@ __global__ void __launch_bounds__(kWarps * 32) dfa_sample_kernel(const SamplePar
                         float2 a2 = make_float2(acc[j][e], acc[j][e + 1]);
 #pragma unroll
                         for (int k = 0; k < 4; ++k)
-                            a2 = __ffma2_rn(make_float2(kk[k], kk[k]), make_float2(r.v[k][j][e], r.v[k][j][e + 1]), a2);
+                            a2 = __ffma2_rn(make_float2(kk[k], kk[k]), make_float2(vv[k][e], vv[k][e + 1]), a2);
                         acc[j][e] = a2.x;
                         acc[j][e + 1] = a2.y;
                     }
@@ -452,7 +473,7 @@ __global__ void __launch_bounds__(kWarps * 32) dfa_sample_kernel(const SamplePar
 #pragma unroll
                     for (int e = 0; e < V; ++e)
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) acc[j][e] = __fmaf_rn(kk[k], r.v[k][j][e], acc[j][e]);
+                        for (int k = 0; k < 4; ++k) acc[j][e] = __fmaf_rn(kk[k], vv[k][e], acc[j][e]);
                 }
             }
         } else {
@@ -465,6 +486,16 @@ __global__ void __launch_bounds__(kWarps * 32) dfa_sample_kernel(const SamplePar
 #pragma unroll
             for (int j = 0; j < NCH; ++j) {
                 // s_k = <grad_out, corner_k> over this lane's channels, then three 4-term forms
+                float vv[4][V];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    if constexpr (kPacked) {
+                        unpack_bf16x8(r.raw[k], vv[k]);
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < V; ++e) vv[k][e] = r.v[k][j][e];
+                    }
+                }
                 float sk[4];
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
@@ -473,12 +504,12 @@ __global__ void __launch_bounds__(kWarps * 32) dfa_sample_kernel(const SamplePar
 #pragma unroll
                         for (int e = 0; e < V; e += 2)
                             s2 = __ffma2_rn(make_float2(go[j][e], go[j][e + 1]),
-                                            make_float2(r.v[k][j][e], r.v[k][j][e + 1]), s2);
+                                            make_float2(vv[k][e], vv[k][e + 1]), s2);
                         sk[k] = s2.x + s2.y;
                     } else {
                         float s1 = 0.f;
 #pragma unroll
-                        for (int e = 0; e < V; ++e) s1 = __fmaf_rn(go[j][e], r.v[k][j][e], s1);
+                        for (int e = 0; e < V; ++e) s1 = __fmaf_rn(go[j][e], vv[k][e], s1);
                         sk[k] = s1;
                     }
                 }
@@ -549,7 +580,22 @@ __global__ void __launch_bounds__(kWarps * 32) dfa_sample_kernel(const SamplePar
         }
     };
 
-    if constexpr (NCH * V <= 8) {
+    if constexpr (kPacked) {   // 4 items deep: 4 x 16 registers of packed rows in flight per lane
+        Item A, B, C_, D_;
+        if (my_items > 0) issue(item_of(0), A);
+        if (my_items > 1) issue(item_of(1), B);
+        if (my_items > 2) issue(item_of(2), C_);
+        for (int q = 0; q < my_items; q += 4) {
+            if (q + 3 < my_items) issue(item_of(q + 3), D_);
+            consume(q, item_of(q), A);
+            if (q + 4 < my_items) issue(item_of(q + 4), A);
+            if (q + 1 < my_items) consume(q + 1, item_of(q + 1), B);
+            if (q + 5 < my_items) issue(item_of(q + 5), B);
+            if (q + 2 < my_items) consume(q + 2, item_of(q + 2), C_);
+            if (q + 6 < my_items) issue(item_of(q + 6), C_);
+            if (q + 3 < my_items) consume(q + 3, item_of(q + 3), D_);
+        }
+    } else if constexpr (NCH * V <= 8) {
         Item A, B;
         if (my_items > 0) issue(item_of(0), A);
         for (int q = 0; q < my_items; q += 2) {
