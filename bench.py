@@ -30,9 +30,26 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
-# keep NCCL's "NCCL version ..." banner (NCCL_DEBUG=VERSION) off stdout: rank 0 prints exactly one JSON line
-if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-    os.environ["NCCL_DEBUG"] = "WARN"
+# stdout carries exactly one JSON line (rank 0).  Libraries write there too (NCCL prints its version banner on
+# stdout under the image's NCCL_DEBUG setting), so file descriptor 1 is pointed at stderr for the whole run and the
+# JSON line goes to the saved descriptor.
+_REAL_STDOUT = None
+
+
+def isolate_stdout():
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    text = json.dumps(line) + "\n"
+    if _REAL_STDOUT is None:
+        sys.stdout.write(text)
+    else:
+        os.write(_REAL_STDOUT, text.encode())
 
 MODALITIES = (("det", 900, 13), ("map", 100, 300), ("plan", 480, 90), ("ego", 1, 13))
 LAYERS = 6
@@ -577,7 +594,7 @@ def gpu_arm(args):
             "kernel_avg_us": {k: round(float(np.mean(v)), 2) for k, v in kern.items()},
             "reference_cuda_op_same_gpu": ref_cuda,
         }
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -645,7 +662,7 @@ def reference_arm(args):
                        "bs_per_gpu": 1},
             "cpu_baseline": r["cpu_baseline"],
             "e2e": {"value": round(r["value"], 4), "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
 
 
 def main():
@@ -663,6 +680,7 @@ def main():
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of CPU baseline work")
     args = ap.parse_args()
+    isolate_stdout()
     if args.impl == "reference":
         reference_arm(args)
     else:
