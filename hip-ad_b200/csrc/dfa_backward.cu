@@ -39,7 +39,7 @@ WorkspaceLayout workspace_layout(const Dims& d) {
     w.cursor = off;  off += align_up((size_t)d.bs * n_cl * sizeof(int));
     w.sortbuf = off; off += align_up((size_t)d.bs * n_cl * 2 * AP * sizeof(unsigned long long));
     // part sums of rows with more than kPart contributions.  Worst case (every sample visible and piled onto few
-    // rows) would need bs*AP*cams*L*8/kPart slots; 1/4 of that covers every realistic input, and a row that finds no
+    // rows) would need bs*AP*cams*L*8/kPart slots; half of that covers every realistic input, and a row that finds no
     // free slots is summed by a single warp instead (dfa_row_classify_kernel).
     w.partial_slots = (size_t)d.bs * (AP * n_cl / 16 + 1024);
     w.part_list = off;   off += align_up(((size_t)d.bs * d.num_feat + w.partial_slots) * kEntryInts * sizeof(int));

@@ -44,7 +44,8 @@ constexpr int kSegScale = 8;             // ints of segment table per feature ro
 constexpr int kClassifyThreads = 256;    // rows classified per CTA (one thread each)
 constexpr int kReduceCtas = 148 * 2;     // persistent CTAs (8 warps, 2 per SM) of the reduce kernel
 constexpr int kTinyRow = 8;              // contributions up to which a row is summed by a quarter warp
-constexpr int kPart = 32;                // contributions per part item (longer rows are split into parts)
+constexpr int kPart = 64;                // contributions per part item (longer rows are split into parts); measured on the
+                                         // stage-2 det / map / plan calls: 32 -> 46 / 76 / 81 us, 64 -> 45 / 68 / 65 us, 128 -> 49 / 73 / 66 us
 constexpr int kMaxChunks = 4096;         // A*P <= 4 Mi samples per batch element
 
 struct GfeatParams {

@@ -564,7 +564,7 @@ def test_config3_sweep_points(ops, oracle_mod, A, P, bf16):
 
 def test_pile_up_on_one_pixel_goes_through_many_parts(ops, oracle_mod):
     """Every sample of every anchor hits the same few pixels: feature rows with thousands of contributions are split
-    into 32-contribution parts whose partial sums are combined in part order (dfa_gfeat_reduce_kernel)."""
+    into 64-contribution parts whose partial sums are combined in part order (dfa_gfeat_reduce_kernel)."""
     case = small_case("c256_g8_l4", seed=50)
     bs, A, P, cams, _ = case["loc"].shape
     rng = np.random.default_rng(5)
@@ -581,7 +581,7 @@ def test_batch_of_eight(ops, oracle_mod):
 
 
 def test_partial_slot_exhaustion_falls_back_to_single_warp_rows(ops, oracle_mod, monkeypatch):
-    """Rows with more than 32 contributions normally go through partial-sum slots; when the pool is exhausted
+    """Rows with more than 64 contributions normally go through partial-sum slots; when the pool is exhausted
     (forced here with HIPAD_DFA_PARTIAL_CAP) such a row is summed by one warp instead, with the same result."""
     case = small_case("c256_g8_l4", seed=51)
     case["loc"] = (0.5 + 0.02 * np.random.default_rng(6).standard_normal(case["loc"].shape)).astype(np.float32)
