@@ -177,10 +177,19 @@ int launch_backward(const BwdArgs& a) {
     gp.d = d;
     gp.seg_stride = wl.seg_stride;
     gp.n_chunks = wl.n_chunks;
-    // enough bands for ~2 sort CTAs per SM, whatever the batch size
+    // enough bands for ~2 sort CTAs per SM, whatever the batch size; twice that for long sample lists, where a band
+    // CTA's cost is the pass over its camera's visible samples (measured, stage-2 map / plan: 24 bands 36 / 40 us
+    // against 42 / 46 us with 12-16; the det call, A*P = 11 700, is 2 us faster with 12)
     const int buckets = d.cams * d.L * d.bs;
     int nb = (2 * 148) / buckets;
+    if ((long long)d.A * d.P >= 24000) nb *= 2;
     gp.NB = nb < 1 ? 1 : (nb > kMaxBands ? kMaxBands : nb);
+    {   // A/B knobs
+        const int fb = hipad_env_int("HIPAD_DFA_BANDS", 0);
+        if (fb >= 1 && fb <= kMaxBands) gp.NB = fb;
+        const int tm = hipad_env_int("HIPAD_DFA_TINY_MAX", kTinyRow);
+        gp.tiny_max = tm < 1 ? 1 : (tm > kTinyRow ? kTinyRow : tm);
+    }
     gp.accumulate = a.accumulate ? 1 : 0;
     gp.tiny_ok = (ks.vector && (d.C == 32 || d.C == 64 || d.C == 128 || d.C == 256) && (d.C / d.G) % 32 == 0 &&
                   hipad_env_int("HIPAD_DFA_TINY", 1) != 0) ? 1 : 0;

@@ -38,7 +38,7 @@ constexpr int kSortWarps = kSortThreads / 32;
 constexpr int kRadixBits = 8;
 constexpr int kRadix = 1 << kRadixBits;
 constexpr int kBandCap = 8192;           // packed words per ping-pong half kept in shared memory
-constexpr int kMaxBands = 16;
+constexpr int kMaxBands = 32;
 constexpr int kScanUnroll = 8;           // independent loads in flight per lane in the band kernel's scans
 constexpr int kSegScale = 8;             // ints of segment table per feature row (upper bound, see seg_offset)
 constexpr int kClassifyThreads = 256;    // rows classified per CTA (one thread each)
@@ -74,6 +74,7 @@ struct GfeatParams {
     int n_chunks;
     int NB;            // requested bands per bucket (<= kMaxBands)
     int accumulate;    // add to the rows already in g_feat instead of overwriting them (shared buffer across calls)
+    int tiny_max;      // rows with at most this many contributions go to the quarter-warp path (<= kTinyRow)
     int tiny_ok;       // shape supported by the quarter-warp kernel (C % 32 == 0, C <= 256, (C/G) % 32 == 0)
 };
 
@@ -598,7 +599,7 @@ __global__ void __launch_bounds__(kClassifyThreads) dfa_row_classify_kernel(cons
                 n = row_segments(p.seg + (size_t)b_idx * p.seg_stride + seg_offset(st), g, y, x, beg, e1, e2, e3);
         }
     }
-    const bool tiny = p.tiny_ok && n > 0 && n <= kTinyRow;
+    const bool tiny = p.tiny_ok && n > 0 && n <= p.tiny_max;
     const bool single = n > 0 && !tiny && n <= kPart, multi = n > kPart;
     const int cam = (cl >= 0) ? cl / d.L : 0;
     const int4 q0 = make_int4(b_idx * d.num_feat + row, n, b_idx, cam | ((cl - cam * d.L) << 8) | (cl << 16));
