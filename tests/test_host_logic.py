@@ -127,3 +127,29 @@ def test_temporal_key_points():
     kp, temp = g(anchor, feat, [T], torch.tensor([1.0, 1.0]), [torch.tensor([0.5, 0.5])])
     expect = kp - (anchor[..., 8:] * 0.5)[:, :, None] + torch.tensor([1.5, 0.0, 0.0])
     assert kp.shape == (2, 5, 4, 3) and torch.allclose(temp[0], expect, atol=1e-5)
+
+
+def test_share_feature_gradient_is_a_no_op_off_the_gpu():
+    """The shared-gradient wiring only exists for CUDA tensors that require grad; anything else passes through."""
+    import hipad_b200
+    x = torch.randn(2, 5, 8, requires_grad=True)
+    assert hipad_b200.share_feature_gradient(x) is x
+    y = torch.randn(2, 5, 8)
+    assert hipad_b200.share_feature_gradient(y) is y
+
+
+def test_reference_arm_prints_one_json_line():
+    """bench.py --impl reference: the reference's CPU torch path, exactly one JSON line on stdout, the contract keys."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1",
+                        "--warmup", "1", "--cpu-budget", "1"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-500:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "GB/s" and d["higher_is_better"] is True
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
