@@ -296,7 +296,8 @@ def gpu_arm(args):
             first = False
 
     # per call: forward sample kernel; backward = sample kernel (+ its own zero-fill kernel when the grid is too
-    # small to fold the fill in: the ego call), visible compaction, band sort, touched-row reduce, heavy-row reduce
+    # small to fold the fill in: the ego call), visible compaction, band sort, row classification, reduce
+    # (stage label "dfa_gfeat_rows+heavy" = classification + reduce kernels)
     launches_per_step = sum(1 + 5 + (1 if bs * c["A"] * 8 < 2 * 148 else 0) for c in calls)
     flush = torch.zeros(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
