@@ -2,6 +2,9 @@
 #include "dfa_dispatch.cuh"
 #include "dfa_gfeat.cuh"
 #include <cstdio>
+#include <map>
+#include <mutex>
+#include <utility>
 
 namespace hipad {
 
@@ -14,6 +17,35 @@ inline int debug_sync(const char* what, cudaStream_t st) {
     if (e != cudaSuccess) fprintf(stderr, "hipad_dfa: %s failed: %s\n", what, cudaGetErrorString(e));
     return (int)e;
 }
+// The compaction -> band sort -> classification chain of a backward call depends only on the sampling locations, not
+// on the sample-major kernel, so it runs beside that kernel on a helper stream (fork / join with events; under CUDA-graph
+// capture the helper stream joins the capture and the two become parallel branches).  One helper stream + two events per
+// (device, caller stream), created on first use outside of any capture and kept for the life of the process.
+struct SideStream {
+    cudaStream_t stream;
+    cudaEvent_t fork, join;
+};
+SideStream* acquire_side_stream(cudaStream_t main) {
+    static std::mutex mu;
+    static std::map<std::pair<int, cudaStream_t>, SideStream> pool;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = pool.find(std::make_pair(dev, main));
+    if (it != pool.end()) return &it->second;
+    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(main, &st) != cudaSuccess) {
+        cudaGetLastError();          // e.g. legacy stream while another stream is capturing: stay serial
+        return nullptr;
+    }
+    if (st != cudaStreamCaptureStatusNone) return nullptr;   // never create resources inside a capture
+    SideStream s;
+    if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    if (cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return &pool.emplace(std::make_pair(dev, main), s).first->second;
+}
+
 constexpr size_t kAlign = 256;
 inline size_t align_up(size_t v) { return (v + kAlign - 1) / kAlign * kAlign; }
 
@@ -127,6 +159,20 @@ int launch_backward(const BwdArgs& a) {
     const size_t smem = sample_smem_for(kBwd, d, ks, a.type, p.PS, warps);
     if (smem > kSampleSmemBudget) return -2;
     const size_t gfeat_bytes = (size_t)d.bs * d.num_feat * d.C * (a.type == kF32 ? 4 : 2);
+    // full backward with a feature gradient: the sort chain goes to the helper stream, forked BEFORE the sample kernel
+    cudaStream_t chain = a.stream;
+    SideStream* side = nullptr;
+    if (a.g_feat != nullptr && a.stage_mask == 7 && !a.classify_only && hipad_env_int("HIPAD_DFA_OVERLAP", 1) != 0 &&
+        hipad_env_int("HIPAD_DFA_DEBUG_SYNC", 0) == 0)
+        side = acquire_side_stream(a.stream);
+    if (side != nullptr) {
+        if (cudaEventRecord(side->fork, a.stream) != cudaSuccess || cudaStreamWaitEvent(side->stream, side->fork, 0) != cudaSuccess) {
+            cudaGetLastError();
+            side = nullptr;
+        } else {
+            chain = side->stream;
+        }
+    }
     if (a.stage_mask & 1) {
         if (a.g_feat != nullptr && !a.accumulate) {
             const bool vec_ok = (gfeat_bytes % 16 == 0) && (reinterpret_cast<uintptr_t>(a.g_feat) % 16 == 0);
@@ -195,27 +241,32 @@ int launch_backward(const BwdArgs& a) {
                   hipad_env_int("HIPAD_DFA_TINY", 1) != 0) ? 1 : 0;
     if (a.stage_mask & 2) {
         dfa_vis_compact_kernel<<<dim3((unsigned)wl.n_chunks, (unsigned)d.cams, (unsigned)d.bs), kVisThreads, 0,
-                                 a.stream>>>(gp);
+                                 chain>>>(gp);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return (int)e;
         const size_t sort_smem = band_sort_smem_bytes(wl.n_chunks);
         e = ensure_smem(dfa_band_sort_kernel, sort_smem);
         if (e != cudaSuccess) return (int)e;
         dfa_band_sort_kernel<<<dim3((unsigned)gp.NB, (unsigned)(d.cams * d.L), (unsigned)d.bs), kSortThreads, sort_smem,
-                               a.stream>>>(gp);
+                               chain>>>(gp);
         e = cudaGetLastError();
         if (e != cudaSuccess) return (int)e;
-        if (int e2 = debug_sync("compaction / band sort", a.stream)) return e2;
+        if (int e2 = debug_sync("compaction / band sort", chain)) return e2;
     }
     if (!(a.stage_mask & 4)) return 0;
 
     // ---- K3: feature-major reduce, overwrites every touched row of the zero-filled g_feat once
     dfa_row_classify_kernel<<<dim3((unsigned)((d.num_feat + kClassifyThreads - 1) / kClassifyThreads), (unsigned)d.bs),
-                              kClassifyThreads, 0, a.stream>>>(gp);
+                              kClassifyThreads, 0, chain>>>(gp);
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
-    if (int e2 = debug_sync("row classification", a.stream)) return e2;
+    if (int e2 = debug_sync("row classification", chain)) return e2;
     if (a.classify_only) return 0;
+    if (side != nullptr) {   // join: the reduce needs the work lists (helper stream) and the zero-filled g_feat (caller's)
+        cudaError_t ej = cudaEventRecord(side->join, side->stream);
+        if (ej == cudaSuccess) ej = cudaStreamWaitEvent(a.stream, side->join, 0);
+        if (ej != cudaSuccess) return (int)ej;
+    }
     const int rc = (a.type == kF32) ? launch_reduce<float>(gp, ks, a.stream) : launch_reduce<__nv_bfloat16>(gp, ks, a.stream);
     if (rc != 0) return rc;
     return debug_sync("feature-gradient reduce", a.stream);

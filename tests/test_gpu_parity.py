@@ -592,3 +592,53 @@ def test_partial_slot_exhaustion_falls_back_to_single_warp_rows(ops, oracle_mod,
     _check_vs_oracle(ops, oracle_mod, case)
     for a, b in zip(ref, got):     # a different summation split for the overflowing rows: equal to fp32 accuracy
         assert rel_err(b, a) <= FP32_TOL
+
+
+def test_backward_under_graph_capture_with_forked_sort_chain(ops, cuda_lib, oracle_mod):
+    """The backward forks its compaction/sort/classify chain onto a helper stream.  Captured in a CUDA graph (helper
+    stream created by the eager warm-up call, so the capture contains the fork and the join) it must reproduce the eager
+    result bit for bit; captured on a stream the library has never seen it stays serial and must do the same."""
+    case = small_case("c256_g8_l4", seed=70)
+    feat, loc, w, go = dev(case["feat"]), dev(case["loc"]), dev(case["weights"]), dev(case["grad_out"])
+    sh, st = dev(case["shapes"]).int(), dev(case["starts"]).int()
+    bs, F, C = feat.shape
+    A, P, cams = loc.shape[1:4]
+    dims = (bs, cams, F, C, sh.shape[1], A, P, w.shape[-1])
+    nb = cuda_lib.hipad_dfa_backward_workspace_bytes(*dims)
+    ws = torch.empty(nb, dtype=torch.uint8, device="cuda")
+
+    def call(stream, g_feat, g_loc, g_w):
+        rc = cuda_lib.hipad_dfa_backward_f32(feat.data_ptr(), sh.data_ptr(), st.data_ptr(), loc.data_ptr(), w.data_ptr(),
+                                             go.data_ptr(), g_feat.data_ptr(), g_loc.data_ptr(), g_w.data_ptr(), *dims,
+                                             ws.data_ptr(), nb, stream.cuda_stream)
+        assert rc == 0
+
+    def buffers():
+        return torch.full_like(feat, 7.0), torch.full_like(loc, 7.0), torch.full_like(w, 7.0)
+
+    torch.cuda.synchronize()
+    results = []
+    for warm in (True, False):
+        s = torch.cuda.Stream()
+        bufs = buffers()
+        with torch.cuda.stream(s):
+            if warm:
+                call(s, *bufs)                      # eager: creates the helper stream of `s`
+                s.synchronize()
+                for b in bufs:
+                    b.fill_(7.0)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=s):
+                call(torch.cuda.current_stream(), *bufs)
+        g.replay()
+        torch.cuda.synchronize()
+        results.append([b.cpu().numpy() for b in bufs])
+    eager = buffers()
+    call(torch.cuda.current_stream(), *eager)
+    torch.cuda.synchronize()
+    r_feat, r_loc, r_w = oracle_mod.backward(case["feat"], case["shapes"], case["starts"], case["loc"], case["weights"],
+                                             case["grad_out"])
+    for got in results:
+        for a, b in zip(got, eager):
+            assert np.array_equal(a, b.cpu().numpy())
+    assert rel_err(results[0][0], r_feat) <= FP32_TOL and rel_err(results[0][1], r_loc) <= FP32_TOL
