@@ -4,9 +4,11 @@
  * This is the drop-in boundary for HiP-AD's hot path.  Every entry point takes
  * plain device pointers + sizes + a CUDA stream and returns an int status
  * (0 = success, >0 = cudaError_t value, <0 = HIPAD_DFA_ERR_*).  No torch types,
- * no global state, no hidden allocation: the caller owns every buffer,
- * including the backward workspace.  All launches go to the given stream and
- * are CUDA-graph capturable (no host synchronisation, no legacy-stream use).
+ * no hidden device allocation: the caller owns every buffer,
+ * including the backward workspace.  All launches go to the given stream (the
+ * backward additionally forks part of its work onto one helper stream per caller
+ * stream, created on first use and joined before the call's last kernel) and are
+ * CUDA-graph capturable (no host synchronisation, no legacy-stream use).
  *
  * Reference interfaces replaced (paths relative to the HiP-AD repository):
  *   projects/mmdet3d_plugin/ops/src/deformable_aggregation_cuda.cu:265-288
