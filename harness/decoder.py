@@ -136,9 +136,10 @@ def load_models(ops="ours"):
     models = importlib.import_module("projects.mmdet3d_plugin.models")
     if want_module:
         import hipad_b200
+        # only the aggregation module is swapped: the instance banks keep using the reference's key-point generators
+        # as anchor handlers (anchor_projection etc. is bank logic, outside the path); our module builds its own
+        # generators (hipad_b200.blocks), whose state-dict keys are the reference's
         regs["ATTENTION"].register_module("DeformableFeatureAggregation", module=hipad_b200.DeformableFeatureAggregation)
-        regs["PLUGIN_LAYERS"].register_module("SparseBox3DKeyPointsGenerator", module=hipad_b200.SparseBox3DKeyPointsGenerator)
-        regs["PLUGIN_LAYERS"].register_module("SparsePoint3DKeyPointsGenerator", module=hipad_b200.SparsePoint3DKeyPointsGenerator)
     return models, regs, counted
 
 
@@ -243,7 +244,7 @@ def use_sdpa_attention(dec):
     torch.nn.functional.scaled_dot_product_attention in the input dtype.  Used for CPU runs of the harness and for
     fp32 parity runs on the GPU (flash-attn's fp16 rounding would otherwise sit between the two op variants)."""
     import torch.nn.functional as F
-    attention = sys.modules["projects.mmdet3d_plugin.models.attention"]
+    attention = dec._hipad_models.attention      # this decoder's own import of models/attention.py
 
     def forward(self, q, kv, causal=False, key_padding_mask=None):
         # q (B,T,H,D), kv (B,S,2,H,D), key_padding_mask (B,S) True = keep

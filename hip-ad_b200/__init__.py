@@ -8,6 +8,7 @@ from .ops import (  # noqa: F401
     DeformableAggregationFunction,
     DeformableAggregationFunctionA800,
     deformable_aggregation_function,
+    deformable_aggregation_group,
     feature_maps_format,
     format_feature_levels,
     fused_deformable_aggregation,

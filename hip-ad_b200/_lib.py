@@ -28,7 +28,35 @@ _SIGNATURES = {
     "hipad_dfa_fused_forward_f32": ([_p] * 9 + _DIMS8 + [_p], _i),
     "hipad_dfa_fused_forward_bf16": ([_p] * 9 + _DIMS8 + [_p], _i),
     "hipad_dfa_format_features": ([_i, _i, _i, _p, _p, _p, _i, _i, _i, _i, _p], _i),
+    "hipad_dfa_group_forward_workspace_bytes": ([_p, _i, _i, _i, _i], ctypes.c_size_t),
+    "hipad_dfa_group_forward": ([_i, _p, _p, _p, _p, _p, _i] + [_i] * 6 + [_p, ctypes.c_size_t, _p], _i),
+    "hipad_dfa_group_backward_workspace_bytes": ([_p, _i] + [_i] * 6, ctypes.c_size_t),
+    "hipad_dfa_group_backward": ([_i, _i, _p, _p, _p, _p, _i, _p, _p] + [_i] * 6 + [_p, ctypes.c_size_t, _p], _i),
+    "hipad_dfa_debug_counters_offset": (_DIMS8, ctypes.c_size_t),
 }
+
+
+class CallT(ctypes.Structure):
+    """hipad_dfa_call_t of include/hipad_dfa.h."""
+    _fields_ = [("sample_location", _p), ("weights", _p), ("grad_sampling_location", _p), ("grad_weights", _p),
+                ("num_anchors", ctypes.c_int32), ("num_pts", ctypes.c_int32)]
+
+
+MAX_GROUP_CALLS = 8
+ERR_UNSUPPORTED = -2
+
+
+def call_table(entries):
+    """entries: list of (loc_ptr, w_ptr, g_loc_ptr or None, g_w_ptr or None, A, P) -> ctypes array of hipad_dfa_call_t"""
+    arr = (CallT * len(entries))()
+    for i, (loc, w, gl, gw, A, P) in enumerate(entries):
+        arr[i].sample_location = loc
+        arr[i].weights = w
+        arr[i].grad_sampling_location = gl
+        arr[i].grad_weights = gw
+        arr[i].num_anchors = A
+        arr[i].num_pts = P
+    return arr
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 
 

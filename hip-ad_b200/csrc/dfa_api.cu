@@ -161,6 +161,81 @@ int hipad_dfa_backward_stages(int feat_is_bf16, int stage_mask, const void* mc_m
                            workspace_bytes, stream, stage_mask & 63);
 }
 
+static int fill_calls(CallDesc* dst, const hipad_dfa_call_t* calls, int num_calls, bool backward) {
+    if (!calls || num_calls < 1 || num_calls > HIPAD_DFA_MAX_GROUP_CALLS) return HIPAD_DFA_ERR_BAD_ARGUMENT;
+    for (int k = 0; k < num_calls; ++k) {
+        const hipad_dfa_call_t& c = calls[k];
+        if (!c.sample_location || !c.weights || c.num_anchors <= 0 || c.num_pts <= 0) return HIPAD_DFA_ERR_BAD_ARGUMENT;
+        if (backward && (!c.grad_sampling_location || !c.grad_weights)) return HIPAD_DFA_ERR_BAD_ARGUMENT;
+        dst[k].loc = c.sample_location; dst[k].weights = c.weights;
+        dst[k].g_loc = c.grad_sampling_location; dst[k].g_w = c.grad_weights;
+        dst[k].A = c.num_anchors; dst[k].P = c.num_pts;
+    }
+    return 0;
+}
+
+size_t hipad_dfa_group_forward_workspace_bytes(const hipad_dfa_call_t* calls, int num_calls, int batch_size,
+                                               int num_cams, int num_embeds) {
+    CallDesc cd[kMaxCalls] = {};
+    if (batch_size <= 0 || num_cams <= 0 || num_embeds <= 0) return 0;
+    if (!calls || num_calls < 1 || num_calls > HIPAD_DFA_MAX_GROUP_CALLS) return 0;
+    for (int k = 0; k < num_calls; ++k) { cd[k].A = calls[k].num_anchors; cd[k].P = calls[k].num_pts; }
+    return group_forward_workspace_bytes(cd, num_calls, batch_size, num_cams, num_embeds);
+}
+
+int hipad_dfa_group_forward(int feat_is_bf16, float* output_packed, const void* mc_ms_feat,
+                            const int32_t* spatial_shape, const int32_t* scale_start_index,
+                            const hipad_dfa_call_t* calls, int num_calls, int batch_size, int num_cams, int num_feat,
+                            int num_embeds, int num_scale, int num_groups, void* workspace, size_t workspace_bytes,
+                            void* stream) {
+    if (!output_packed || !mc_ms_feat || !spatial_shape || !scale_start_index ||
+        bad_dims(batch_size, num_cams, num_feat, num_embeds, num_scale, 1, 1, num_groups))
+        return HIPAD_DFA_ERR_BAD_ARGUMENT;
+    GroupFwdArgs a = {};
+    if (int rc = fill_calls(a.calls, calls, num_calls, false)) return rc;
+    a.type = feat_is_bf16 ? kBF16 : kF32; a.out = output_packed; a.feat = mc_ms_feat;
+    a.shapes = spatial_shape; a.starts = scale_start_index; a.ncalls = num_calls;
+    a.bs = batch_size; a.cams = num_cams; a.num_feat = num_feat; a.C = num_embeds; a.L = num_scale; a.G = num_groups;
+    a.workspace = workspace; a.workspace_bytes = workspace_bytes;
+    a.stream = reinterpret_cast<cudaStream_t>(stream);
+    return launch_group_forward(a);
+}
+
+size_t hipad_dfa_group_backward_workspace_bytes(const hipad_dfa_call_t* calls, int num_calls, int batch_size,
+                                                int num_cams, int num_feat, int num_embeds, int num_scale,
+                                                int num_groups) {
+    CallDesc cd[kMaxCalls] = {};
+    if (bad_dims(batch_size, num_cams, num_feat, num_embeds, num_scale, 1, 1, num_groups)) return 0;
+    if (!calls || num_calls < 1 || num_calls > HIPAD_DFA_MAX_GROUP_CALLS) return 0;
+    for (int k = 0; k < num_calls; ++k) {
+        if (calls[k].num_anchors <= 0 || calls[k].num_pts <= 0) return 0;
+        cd[k].A = calls[k].num_anchors; cd[k].P = calls[k].num_pts;
+    }
+    return group_backward_workspace_bytes(cd, num_calls, batch_size, num_cams, num_feat, num_embeds, num_scale, num_groups);
+}
+
+int hipad_dfa_group_backward(int feat_is_bf16, int grad_feat_flags, const void* mc_ms_feat,
+                             const int32_t* spatial_shape, const int32_t* scale_start_index,
+                             const hipad_dfa_call_t* calls, int num_calls, const float* grad_output_packed,
+                             void* grad_mc_ms_feat, int batch_size, int num_cams, int num_feat, int num_embeds,
+                             int num_scale, int num_groups, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!mc_ms_feat || !spatial_shape || !scale_start_index || !grad_output_packed ||
+        bad_dims(batch_size, num_cams, num_feat, num_embeds, num_scale, 1, 1, num_groups))
+        return HIPAD_DFA_ERR_BAD_ARGUMENT;
+    if ((grad_feat_flags & 1) && !grad_mc_ms_feat) return HIPAD_DFA_ERR_BAD_ARGUMENT;
+    GroupBwdArgs a = {};
+    if (int rc = fill_calls(a.calls, calls, num_calls, true)) return rc;
+    a.type = feat_is_bf16 ? kBF16 : kF32; a.feat = mc_ms_feat; a.shapes = spatial_shape; a.starts = scale_start_index;
+    a.ncalls = num_calls; a.grad_out = grad_output_packed; a.g_feat = grad_mc_ms_feat;
+    a.accumulate = (grad_feat_flags & 1) != 0;
+    a.g_feat_f32 = !feat_is_bf16 || (grad_feat_flags & 2) != 0;
+    a.bs = batch_size; a.cams = num_cams; a.num_feat = num_feat; a.C = num_embeds; a.L = num_scale; a.G = num_groups;
+    a.workspace = workspace; a.workspace_bytes = workspace_bytes;
+    a.stream = reinterpret_cast<cudaStream_t>(stream);
+    a.stage_mask = 7;
+    return launch_group_backward(a);
+}
+
 int hipad_dfa_sample_indices(int32_t* indices, const int32_t* spatial_shape, const int32_t* scale_start_index,
                              const float* sample_location, int batch_size, int num_cams, int num_scale,
                              int num_anchors, int num_pts, void* stream) {

@@ -1,6 +1,8 @@
 // dfa_backward.cu — backward launchers: sample-major (g_w, g_loc) + feature-major (g_feat).
 #include "dfa_dispatch.cuh"
 #include "dfa_gfeat.cuh"
+#include "dfa_group.cuh"
+#include "dfa_group_host.h"
 #include <cstdio>
 #include <map>
 #include <mutex>
@@ -28,6 +30,9 @@ struct SideStream {
 SideStream* acquire_side_stream(cudaStream_t main) {
     static std::mutex mu;
     static std::map<std::pair<int, cudaStream_t>, SideStream> pool;
+    // cudaStreamPerThread names a different stream in every host thread: one pool entry (one event pair) would be
+    // shared by all of them, so such callers stay serial.  A given caller stream must be driven by one thread at a time.
+    if (main == cudaStreamPerThread) return nullptr;
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
     std::lock_guard<std::mutex> lock(mu);
@@ -50,33 +55,51 @@ constexpr size_t kAlign = 256;
 inline size_t align_up(size_t v) { return (v + kAlign - 1) / kAlign * kAlign; }
 
 struct WorkspaceLayout {
-    size_t vis_id, vis_xy, vis_cnt, band_cnt, rec, seg, cursor, sortbuf, part_list, tiny_list, partial, unit_done, counters, total;
+    size_t vis_id, vis_xy, vis_cnt, band_cnt, rec, recw, seg, cursor, sortbuf, part_list, tiny_list, partial, unit_done, counters, total;
     size_t partial_slots;
     int seg_stride, n_chunks;
 };
 
-WorkspaceLayout workspace_layout(const Dims& d) {
+// sample id space of a group: call k owns [id_begin[k], id_begin[k] + A*P), id_begin a multiple of kVisChunk
+struct IdSpace {
+    int id_begin[kMaxCalls], anchor_begin[kMaxCalls];
+    long long n_ids, a_total;
+};
+IdSpace id_space(const CallDesc* calls, int ncalls) {
+    IdSpace s = {};
+    for (int k = 0; k < ncalls; ++k) {
+        s.id_begin[k] = (int)s.n_ids;
+        s.anchor_begin[k] = (int)s.a_total;
+        const long long ap = (long long)calls[k].A * calls[k].P;
+        s.n_ids += (ap + kVisChunk - 1) / kVisChunk * kVisChunk;
+        s.a_total += calls[k].A;
+    }
+    return s;
+}
+
+WorkspaceLayout workspace_layout(int bs, int cams, int num_feat, int C, int L, int G, long long n_ids) {
     WorkspaceLayout w;
-    const size_t n_cl = (size_t)d.cams * d.L, AP = (size_t)d.A * d.P;
-    w.n_chunks = (int)((AP + kVisChunk - 1) / kVisChunk);
+    const size_t n_cl = (size_t)cams * L, AP = (size_t)n_ids;
+    w.n_chunks = (int)(AP / kVisChunk);
     // band tables of a bucket occupy [8*start, 8*(start + h*w)) (dfa_gfeat.cuh, seg_offset)
-    w.seg_stride = (int)((size_t)kSegScale * d.num_feat);
+    w.seg_stride = (int)((size_t)kSegScale * num_feat);
     size_t off = 0;
-    w.vis_id = off;  off += align_up((size_t)d.bs * d.cams * AP * sizeof(int));
-    w.vis_xy = off;  off += align_up((size_t)d.bs * d.cams * AP * sizeof(float2));
-    w.vis_cnt = off; off += align_up((size_t)d.bs * d.cams * w.n_chunks * sizeof(int));
-    w.band_cnt = off; off += align_up((size_t)d.bs * d.cams * w.n_chunks * d.L * kMaxBands * sizeof(int));
-    w.rec = off;     off += align_up((size_t)d.bs * n_cl * AP * sizeof(int4));
-    w.seg = off;     off += align_up((size_t)d.bs * w.seg_stride * sizeof(int));
-    w.cursor = off;  off += align_up((size_t)d.bs * n_cl * sizeof(int));
-    w.sortbuf = off; off += align_up((size_t)d.bs * n_cl * 2 * AP * sizeof(unsigned long long));
+    w.vis_id = off;  off += align_up((size_t)bs * cams * AP * sizeof(int));
+    w.vis_xy = off;  off += align_up((size_t)bs * cams * AP * sizeof(float2));
+    w.vis_cnt = off; off += align_up((size_t)bs * cams * w.n_chunks * sizeof(int));
+    w.band_cnt = off; off += align_up((size_t)bs * cams * w.n_chunks * L * kMaxBands * sizeof(int));
+    w.rec = off;     off += align_up((size_t)bs * n_cl * AP * sizeof(int4));
+    w.recw = off;    off += align_up((size_t)bs * n_cl * AP * G * sizeof(float));
+    w.seg = off;     off += align_up((size_t)bs * w.seg_stride * sizeof(int));
+    w.cursor = off;  off += align_up((size_t)bs * n_cl * sizeof(int));
+    w.sortbuf = off; off += align_up((size_t)bs * n_cl * 2 * AP * sizeof(unsigned long long));
     // part sums of rows with more than kPart contributions.  Worst case (every sample visible and piled onto few
     // rows) would need bs*AP*cams*L*8/kPart slots; half of that covers every realistic input, and a row that finds no
     // free slots is summed by a single warp instead (dfa_row_classify_kernel).
-    w.partial_slots = (size_t)d.bs * (AP * n_cl / 16 + 1024);
-    w.part_list = off;   off += align_up(((size_t)d.bs * d.num_feat + w.partial_slots) * kEntryInts * sizeof(int));
-    w.tiny_list = off;   off += align_up((size_t)d.bs * d.num_feat * kEntryInts * sizeof(int));
-    w.partial = off;     off += align_up(w.partial_slots * d.C * sizeof(float));
+    w.partial_slots = (size_t)bs * (AP * n_cl / 16 + 1024);
+    w.part_list = off;   off += align_up(((size_t)bs * num_feat + w.partial_slots) * kEntryInts * sizeof(int));
+    w.tiny_list = off;   off += align_up((size_t)bs * num_feat * kEntryInts * sizeof(int));
+    w.partial = off;     off += align_up(w.partial_slots * C * sizeof(float));
     w.unit_done = off;   off += align_up(w.partial_slots * sizeof(int));
     w.counters = off;    off += align_up(8 * sizeof(int));
     w.total = off;
@@ -122,44 +145,71 @@ int launch_reduce(const GfeatParams& gp, KernelShape ks, cudaStream_t st) {
 }
 }  // namespace
 
-size_t backward_workspace_bytes(const Dims& d) { return workspace_layout(d).total; }
-size_t backward_counters_offset(const Dims& d) { return workspace_layout(d).counters; }
+size_t group_backward_workspace_bytes(const CallDesc* calls, int ncalls, int bs, int cams, int num_feat, int C, int L, int G) {
+    if (ncalls < 1 || ncalls > kMaxCalls) return 0;
+    return workspace_layout(bs, cams, num_feat, C, L, G, id_space(calls, ncalls).n_ids).total;
+}
+size_t group_backward_counters_offset(const CallDesc* calls, int ncalls, int bs, int cams, int num_feat, int C, int L, int G) {
+    if (ncalls < 1 || ncalls > kMaxCalls) return 0;
+    return workspace_layout(bs, cams, num_feat, C, L, G, id_space(calls, ncalls).n_ids).counters;
+}
+size_t backward_workspace_bytes(const Dims& d) {
+    CallDesc c = {}; c.A = d.A; c.P = d.P;
+    return group_backward_workspace_bytes(&c, 1, d.bs, d.cams, d.num_feat, d.C, d.L, d.G);
+}
+size_t backward_counters_offset(const Dims& d) {
+    CallDesc c = {}; c.A = d.A; c.P = d.P;
+    return group_backward_counters_offset(&c, 1, d.bs, d.cams, d.num_feat, d.C, d.L, d.G);
+}
 
-int launch_backward(const BwdArgs& a) {
-    const Dims& d = a.d;
-    const bool al = (reinterpret_cast<uintptr_t>(a.feat) % 16 == 0) &&
-                    (reinterpret_cast<uintptr_t>(a.g_feat) % 16 == 0) &&   /* nullptr passes */
-                    (reinterpret_cast<uintptr_t>(a.grad_out) % 16 == 0) &&
-                    (reinterpret_cast<uintptr_t>(a.g_w) % 16 == 0);
+int launch_backward(const BwdArgs& b) {
+    GroupBwdArgs a = {};
+    a.type = b.type; a.feat = b.feat; a.shapes = b.shapes; a.starts = b.starts;
+    a.calls[0].loc = b.loc; a.calls[0].weights = b.weights; a.calls[0].g_loc = b.g_loc; a.calls[0].g_w = b.g_w;
+    a.calls[0].A = b.d.A; a.calls[0].P = b.d.P;
+    a.ncalls = 1;
+    a.grad_out = b.grad_out; a.g_feat = b.g_feat; a.g_feat_f32 = (b.type == kF32); a.accumulate = b.accumulate;
+    a.bs = b.d.bs; a.cams = b.d.cams; a.num_feat = b.d.num_feat; a.C = b.d.C; a.L = b.d.L; a.G = b.d.G;
+    a.workspace = b.workspace; a.workspace_bytes = b.workspace_bytes; a.stream = b.stream;
+    a.stage_mask = b.stage_mask; a.classify_only = b.classify_only; a.separate_zero_fill = b.separate_zero_fill;
+    return launch_group_backward(a);
+}
+
+int launch_group_backward(const GroupBwdArgs& a) {
+    if (a.ncalls < 1 || a.ncalls > kMaxCalls) return -1;
+    Dims d = {};
+    d.bs = a.bs; d.cams = a.cams; d.num_feat = a.num_feat; d.C = a.C; d.L = a.L; d.G = a.G;
+    d.A = a.calls[0].A; d.P = a.calls[0].P;       // per-call kernels only (single call / bs == 1 fallback)
+    bool al = (reinterpret_cast<uintptr_t>(a.feat) % 16 == 0) &&
+              (reinterpret_cast<uintptr_t>(a.g_feat) % 16 == 0) &&   /* nullptr passes */
+              (reinterpret_cast<uintptr_t>(a.grad_out) % 16 == 0);
+    for (int k = 0; k < a.ncalls; ++k) {
+        const CallDesc& c = a.calls[k];
+        if (!c.loc || !c.weights || !c.g_loc || !c.g_w || c.A <= 0 || c.P <= 0) return -1;
+        // float2 / float4 accesses of the kernels (reject instead of faulting on odd sub-buffers)
+        if (reinterpret_cast<uintptr_t>(c.loc) % 8 != 0 || reinterpret_cast<uintptr_t>(c.g_loc) % 8 != 0) return -1;
+        al = al && (reinterpret_cast<uintptr_t>(c.g_w) % 16 == 0) && (reinterpret_cast<uintptr_t>(c.weights) % 16 == 0);
+        if ((long long)c.A * c.P > (long long)kMaxChunks * kVisChunk) return -2;
+        if ((long long)c.A * c.P * d.cams * d.L * d.G >= (1LL << 30)) return -2;
+    }
     const KernelShape ks = pick_shape(a.type, d.C, d.G, al);
-    if (!ks.ok || d.cams * d.L > kMaxCamLevels || (long long)d.num_feat * d.C >= (1LL << 30)) return -2;
-    const WorkspaceLayout wl = workspace_layout(d);
+    const KernelShape ks_g = a.g_feat_f32 ? pick_shape(kF32, d.C, d.G, al) : ks;     // lane map of the reduce
+    if (!ks.ok || !ks_g.ok || d.cams * d.L > kMaxCamLevels || (long long)d.num_feat * d.C >= (1LL << 30)) return -2;
+    const IdSpace ids = id_space(a.calls, a.ncalls);
+    if (ids.n_ids > (long long)kMaxChunks * kVisChunk || ids.a_total * d.C >= (1LL << 30)) return -2;
+    const WorkspaceLayout wl = workspace_layout(d.bs, d.cams, d.num_feat, d.C, d.L, d.G, ids.n_ids);
     if (a.g_feat != nullptr &&
         (a.workspace == nullptr || a.workspace_bytes < wl.total ||
          reinterpret_cast<uintptr_t>(a.workspace) % kAlign != 0))
         return -3;
-    if ((long long)d.A * d.P > (long long)kMaxChunks * kVisChunk) return -2;
-    // 32-bit BYTE offsets inside one batch element's weights / grad_out (dfa_gfeat.cuh, accumulate_row)
-    if ((long long)d.A * d.P * d.cams * d.L * d.G >= (1LL << 30) || (long long)d.A * d.C >= (1LL << 30)) return -2;
+    if (d.bs > 65535 || (long long)d.bs * d.num_feat >= (1LL << 31)) return -2;
+    const bool grouped = al && group_kernel_supported(a.type, d.C, d.L, d.G, d.cams);
+    if (!grouped && a.ncalls > 1 && d.bs > 1) return -2;     // per-call kernels need contiguous [bs, A, C] gradients
 
-    // ---- K1: sample-major, g_w + g_loc (fully written); zero-fills g_feat on the side when it has the CTAs
-    SampleParams p = {};
-    p.feat = a.feat; p.shapes = a.shapes; p.starts = a.starts;
-    p.loc = a.loc; p.weights = a.weights;
-    p.grad_out = a.grad_out; p.g_loc = a.g_loc; p.g_w = a.g_w;
-    p.d = d;
-    const int NP = d.P * d.cams;
-    const long long rows = (long long)d.bs * d.A;
-    p.S = choose_slices(rows, NP, 8 * 148, sample_smem_per_pair(kBwd, d.L), /*max_slices=*/1 << 20);
-    if (p.S == 0 || d.bs > 65535 || (long long)d.bs * d.num_feat >= (1LL << 31)) return -2;
-    p.PS = (NP + p.S - 1) / p.S;
-    const long long grid = rows * p.S;
-    if (grid > 0x7fffffffLL) return -2;
-    const int warps = choose_sample_warps(grid, d.G);
-    const size_t smem = sample_smem_for(kBwd, d, ks, a.type, p.PS, warps);
-    if (smem > kSampleSmemBudget) return -2;
-    const size_t gfeat_bytes = (size_t)d.bs * d.num_feat * d.C * (a.type == kF32 ? 4 : 2);
+    const size_t gfeat_elem = (a.g_feat_f32 || a.type == kF32) ? 4 : 2;
+    const size_t gfeat_bytes = (size_t)d.bs * d.num_feat * d.C * gfeat_elem;
     // full backward with a feature gradient: the sort chain goes to the helper stream, forked BEFORE the sample kernel
+    // (every fallible check is above this point, so a fork is always followed by its join)
     cudaStream_t chain = a.stream;
     SideStream* side = nullptr;
     if (a.g_feat != nullptr && a.stage_mask == 7 && !a.classify_only && hipad_env_int("HIPAD_DFA_OVERLAP", 1) != 0 &&
@@ -173,40 +223,105 @@ int launch_backward(const BwdArgs& a) {
             chain = side->stream;
         }
     }
+    // joins the helper stream back into the caller's on every exit path after a successful fork
+    auto finish = [&](int rc) {
+        if (side != nullptr) {
+            cudaError_t ej = cudaEventRecord(side->join, side->stream);
+            if (ej == cudaSuccess) ej = cudaStreamWaitEvent(a.stream, side->join, 0);
+            side = nullptr;
+            if (rc == 0 && ej != cudaSuccess) rc = (int)ej;
+        }
+        return rc;
+    };
+
+    // ---- K1: sample-major, g_w + g_loc (fully written); zero-fills g_feat on the side when it has the CTAs
     if (a.stage_mask & 1) {
-        if (a.g_feat != nullptr && !a.accumulate) {
-            const bool vec_ok = (gfeat_bytes % 16 == 0) && (reinterpret_cast<uintptr_t>(a.g_feat) % 16 == 0);
-            if (vec_ok && grid >= 2 * 148 && !a.separate_zero_fill) {
-                p.zero_ptr = reinterpret_cast<uint4*>(a.g_feat);
-                p.zero_n16 = (long long)(gfeat_bytes / 16);
-            } else if (vec_ok) {
-                dfa_zero_kernel<<<148 * 16, 256, 0, a.stream>>>(reinterpret_cast<uint4*>(a.g_feat),
-                                                              (long long)(gfeat_bytes / 16));
-                const cudaError_t e = cudaGetLastError();
-                if (e != cudaSuccess) return (int)e;
-            } else {
-                const cudaError_t e = cudaMemsetAsync(a.g_feat, 0, gfeat_bytes, a.stream);
-                if (e != cudaSuccess) return (int)e;
+        const bool want_zero = a.g_feat != nullptr && !a.accumulate;
+        const bool vec_ok = (gfeat_bytes % 16 == 0) && (reinterpret_cast<uintptr_t>(a.g_feat) % 16 == 0);
+        bool zero_done = !want_zero;
+        auto separate_zero = [&]() -> int {
+            if (vec_ok) {
+                dfa_zero_kernel<<<148 * 16, 256, 0, a.stream>>>(reinterpret_cast<uint4*>(a.g_feat), (long long)(gfeat_bytes / 16));
+                return (int)cudaGetLastError();
+            }
+            return (int)cudaMemsetAsync(a.g_feat, 0, gfeat_bytes, a.stream);
+        };
+        if (grouped) {
+            const GroupPlan pl = plan_group(true, a.calls, a.ncalls, d.bs, d.cams, d.C, 0);
+            GroupParams gpk = {};
+            gpk.feat = a.feat; gpk.shapes = a.shapes; gpk.starts = a.starts;
+            int rc = fill_group_params(gpk, pl, a.calls, a.ncalls, d.bs, d.cams, d.num_feat, d.C, d.G,
+                                       ids.a_total * d.C, nullptr, a.grad_out);
+            if (rc != 0) return finish(rc);
+            if (want_zero) {
+                if (vec_ok && pl.units >= 2 * 148 && !a.separate_zero_fill) {
+                    gpk.zero_ptr = reinterpret_cast<uint4*>(a.g_feat);
+                    gpk.zero_n16 = (long long)(gfeat_bytes / 16);
+                } else if (int e = separate_zero()) {
+                    return finish(e);
+                }
+                zero_done = true;
+            }
+            rc = launch_group_sample(true, a.type, gpk, pl.units, a.stream);
+            if (rc != 0) return finish(rc);
+        } else {
+            for (int k = 0; k < a.ncalls; ++k) {
+                Dims dk = d;
+                dk.A = a.calls[k].A; dk.P = a.calls[k].P;
+                SampleParams p = {};
+                p.feat = a.feat; p.shapes = a.shapes; p.starts = a.starts;
+                p.loc = a.calls[k].loc; p.weights = a.calls[k].weights;
+                p.grad_out = a.grad_out + (size_t)ids.anchor_begin[k] * d.C;     // ncalls == 1 or bs == 1: contiguous
+                p.g_loc = a.calls[k].g_loc; p.g_w = a.calls[k].g_w;
+                p.d = dk;
+                const int NP = dk.P * dk.cams;
+                const long long rows = (long long)dk.bs * dk.A;
+                p.S = choose_slices(rows, NP, 8 * 148, sample_smem_per_pair(kBwd, dk.L), /*max_slices=*/1 << 20);
+                if (p.S == 0) return finish(-2);
+                p.PS = (NP + p.S - 1) / p.S;
+                const long long grid = rows * p.S;
+                if (grid > 0x7fffffffLL) return finish(-2);
+                const int warps = choose_sample_warps(grid, dk.G);
+                const size_t smem = sample_smem_for(kBwd, dk, ks, a.type, p.PS, warps);
+                if (smem > kSampleSmemBudget) return finish(-2);
+                if (!zero_done) {
+                    if (vec_ok && grid >= 2 * 148 && !a.separate_zero_fill) {
+                        p.zero_ptr = reinterpret_cast<uint4*>(a.g_feat);
+                        p.zero_n16 = (long long)(gfeat_bytes / 16);
+                    } else if (int e = separate_zero()) {
+                        return finish(e);
+                    }
+                    zero_done = true;
+                }
+                const int rc = (a.type == kF32)
+                                   ? dispatch_sample<float, kBwd, false>(p, ks, warps, (int)grid, smem, a.stream)
+                                   : dispatch_sample<__nv_bfloat16, kBwd, false>(p, ks, warps, (int)grid, smem, a.stream);
+                if (rc != 0) return finish(rc);
             }
         }
-        const int rc = (a.type == kF32)
-                           ? dispatch_sample<float, kBwd, false>(p, ks, warps, (int)grid, smem, a.stream)
-                           : dispatch_sample<__nv_bfloat16, kBwd, false>(p, ks, warps, (int)grid, smem, a.stream);
-        if (rc != 0) return rc;
-        if (int e = debug_sync("sample-major backward kernel", a.stream)) return e;
+        if (int e = debug_sync("sample-major backward kernel", a.stream)) return finish(e);
     }
-    if (a.g_feat == nullptr) return 0;   // caller does not need the feature-map gradient
+    if (a.g_feat == nullptr) return finish(0);   // caller does not need the feature-map gradient
 
     // ---- K2: visible-sample compaction, then per-(b,cam,level,band) sort by quad key
     unsigned char* ws = reinterpret_cast<unsigned char*>(a.workspace);
     GfeatParams gp = {};
-    gp.shapes = a.shapes; gp.starts = a.starts; gp.loc = a.loc; gp.weights = a.weights;
+    gp.shapes = a.shapes; gp.starts = a.starts;
+    gp.ncalls = a.ncalls;
+    for (int k = 0; k < a.ncalls; ++k) {
+        gp.calls[k].loc = a.calls[k].loc; gp.calls[k].weights = a.calls[k].weights;
+        gp.calls[k].A = a.calls[k].A; gp.calls[k].P = a.calls[k].P;
+        gp.calls[k].id_begin = ids.id_begin[k]; gp.calls[k].anchor_begin = ids.anchor_begin[k];
+    }
+    gp.n_ids = (int)ids.n_ids;
+    gp.A_total = (int)ids.a_total;
     gp.grad_out = a.grad_out; gp.g_feat = a.g_feat;
     gp.vis_id = reinterpret_cast<int*>(ws + wl.vis_id);
     gp.vis_xy = reinterpret_cast<float2*>(ws + wl.vis_xy);
     gp.vis_cnt = reinterpret_cast<int*>(ws + wl.vis_cnt);
     gp.band_cnt = reinterpret_cast<int*>(ws + wl.band_cnt);
     gp.rec = reinterpret_cast<int4*>(ws + wl.rec);
+    gp.recw = reinterpret_cast<float*>(ws + wl.recw);
     gp.seg = reinterpret_cast<int*>(ws + wl.seg);
     gp.cursor = reinterpret_cast<int*>(ws + wl.cursor);
     gp.sortbuf = reinterpret_cast<unsigned long long*>(ws + wl.sortbuf);
@@ -228,7 +343,7 @@ int launch_backward(const BwdArgs& a) {
     // against 42 / 46 us with 12-16; the det call, A*P = 11 700, is 2 us faster with 12)
     const int buckets = d.cams * d.L * d.bs;
     int nb = (2 * 148) / buckets;
-    if ((long long)d.A * d.P >= 24000) nb *= 2;
+    if (ids.n_ids >= 24000) nb *= 2;
     gp.NB = nb < 1 ? 1 : (nb > kMaxBands ? kMaxBands : nb);
     {   // A/B knobs
         const int fb = hipad_env_int("HIPAD_DFA_BANDS", 0);
@@ -237,37 +352,35 @@ int launch_backward(const BwdArgs& a) {
         gp.tiny_max = tm < 1 ? 1 : (tm > kTinyRow ? kTinyRow : tm);
     }
     gp.accumulate = a.accumulate ? 1 : 0;
-    gp.tiny_ok = (ks.vector && (d.C == 32 || d.C == 64 || d.C == 128 || d.C == 256) && (d.C / d.G) % 32 == 0 &&
+    gp.tiny_ok = (ks_g.vector && (d.C == 32 || d.C == 64 || d.C == 128 || d.C == 256) && (d.C / d.G) % 32 == 0 &&
                   hipad_env_int("HIPAD_DFA_TINY", 1) != 0) ? 1 : 0;
     if (a.stage_mask & 2) {
         dfa_vis_compact_kernel<<<dim3((unsigned)wl.n_chunks, (unsigned)d.cams, (unsigned)d.bs), kVisThreads, 0,
                                  chain>>>(gp);
         cudaError_t e = cudaGetLastError();
-        if (e != cudaSuccess) return (int)e;
+        if (e != cudaSuccess) return finish((int)e);
         const size_t sort_smem = band_sort_smem_bytes(wl.n_chunks);
         e = ensure_smem(dfa_band_sort_kernel, sort_smem);
-        if (e != cudaSuccess) return (int)e;
+        if (e != cudaSuccess) return finish((int)e);
         dfa_band_sort_kernel<<<dim3((unsigned)gp.NB, (unsigned)(d.cams * d.L), (unsigned)d.bs), kSortThreads, sort_smem,
                                chain>>>(gp);
         e = cudaGetLastError();
-        if (e != cudaSuccess) return (int)e;
-        if (int e2 = debug_sync("compaction / band sort", chain)) return e2;
+        if (e != cudaSuccess) return finish((int)e);
+        if (int e2 = debug_sync("compaction / band sort", chain)) return finish(e2);
     }
-    if (!(a.stage_mask & 4)) return 0;
+    if (!(a.stage_mask & 4)) return finish(0);
 
     // ---- K3: feature-major reduce, overwrites every touched row of the zero-filled g_feat once
     dfa_row_classify_kernel<<<dim3((unsigned)((d.num_feat + kClassifyThreads - 1) / kClassifyThreads), (unsigned)d.bs),
                               kClassifyThreads, 0, chain>>>(gp);
     const cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return (int)e;
-    if (int e2 = debug_sync("row classification", chain)) return e2;
-    if (a.classify_only) return 0;
-    if (side != nullptr) {   // join: the reduce needs the work lists (helper stream) and the zero-filled g_feat (caller's)
-        cudaError_t ej = cudaEventRecord(side->join, side->stream);
-        if (ej == cudaSuccess) ej = cudaStreamWaitEvent(a.stream, side->join, 0);
-        if (ej != cudaSuccess) return (int)ej;
-    }
-    const int rc = (a.type == kF32) ? launch_reduce<float>(gp, ks, a.stream) : launch_reduce<__nv_bfloat16>(gp, ks, a.stream);
+    if (e != cudaSuccess) return finish((int)e);
+    if (int e2 = debug_sync("row classification", chain)) return finish(e2);
+    if (a.classify_only) return finish(0);
+    // join: the reduce needs the work lists (helper stream) and the zero-filled g_feat (caller's)
+    if (int ej = finish(0)) return ej;
+    const int rc = (a.type == kF32 || a.g_feat_f32) ? launch_reduce<float>(gp, ks_g, a.stream)
+                                                    : launch_reduce<__nv_bfloat16>(gp, ks_g, a.stream);
     if (rc != 0) return rc;
     return debug_sync("feature-gradient reduce", a.stream);
 }

@@ -53,6 +53,17 @@ int launch_forward(const FwdArgs& a) {
     if (!ks.ok || d.cams * d.L > kMaxCamLevels || (long long)d.num_feat * d.C >= (1LL << 30)) return -2;
     const int mode = a.fused ? kFused : kFwd;
     if (a.fused && (256 % d.G != 0)) return -2;
+    if (!a.fused && al && d.P * d.cams <= 128 && group_kernel_supported(a.type, d.C, d.L, d.G, d.cams)) {
+        // whole rows fit one work unit: the grouped kernel (dfa_group.cuh) with a single call and no workspace
+        GroupFwdArgs g = {};
+        g.type = a.type; g.out = a.out; g.feat = a.feat; g.shapes = a.shapes; g.starts = a.starts;
+        g.calls[0].loc = a.loc; g.calls[0].weights = a.weights; g.calls[0].A = d.A; g.calls[0].P = d.P;
+        g.ncalls = 1;
+        g.bs = d.bs; g.cams = d.cams; g.num_feat = d.num_feat; g.C = d.C; g.L = d.L; g.G = d.G;
+        g.stream = a.stream;
+        const int rc = launch_group_forward(g);
+        if (rc != -2) return rc;
+    }
 
     SampleParams p = {};
     p.feat = a.feat; p.shapes = a.shapes; p.starts = a.starts;

@@ -48,21 +48,36 @@ constexpr int kPart = 64;                // contributions per part item (longer 
                                          // stage-2 det / map / plan calls: 32 -> 46 / 76 / 81 us, 64 -> 45 / 68 / 65 us, 128 -> 49 / 73 / 66 us
 constexpr int kMaxChunks = 4096;         // A*P <= 4 Mi samples per batch element
 
+// One aggregation call of a group (all calls of a group read the same feature maps and share ONE feature gradient).
+// Samples of the group live in one id space: call k owns ids [id_begin, id_begin + A*P), id_begin a multiple of
+// kVisChunk, so a compaction chunk never straddles two calls.
+constexpr int kMaxGfeatCalls = 8;
+struct GfeatCall {
+    const float* loc;        // [bs, A, P, cams, 2]
+    const float* weights;    // [bs, A, P, cams, L, G]
+    int A, P;
+    int id_begin;            // first sample id of this call in the group's id space
+    int anchor_begin;        // first row of this call in the packed grad_out [bs, A_total, C]
+};
+
 struct GfeatParams {
     const int* shapes;
     const int* starts;
-    const float* loc;
-    const float* weights;
-    const float* grad_out;
+    GfeatCall calls[kMaxGfeatCalls];
+    int ncalls;
+    int n_ids;         // size of the group's sample id space (sum of the calls' A*P rounded up to kVisChunk)
+    int A_total;       // rows per batch element of the packed grad_out
+    const float* grad_out;   // [bs, A_total, C]
     void* g_feat;
-    int* vis_id;       // [bs][cams][A*P]      compacted visible sample ids, chunk c at [c*kVisChunk, ...)
-    float2* vis_xy;    // [bs][cams][A*P]      their locations
+    int* vis_id;       // [bs][cams][n_ids]    compacted visible sample ids, chunk c at [c*kVisChunk, ...)
+    float2* vis_xy;    // [bs][cams][n_ids]    their locations
     int* vis_cnt;      // [bs][cams][n_chunks] visible samples per chunk
     int* band_cnt;     // [bs][cams][n_chunks][L][kMaxBands] of them, per level, the ones whose quad row falls into each band
-    int4* rec;         // [bs][cams*L][A*P]    sorted records {sample, anchor, lh, lw}
+    int4* rec;         // [bs][cams*L][n_ids]  sorted records {sample id, packed anchor row, lh, lw}
+    float* recw;       // [bs][cams*L][n_ids][G] the G weights of each record's (sample, cam, level), in record order
     int* seg;          // [bs][seg_stride]     segment tables (absolute positions inside the bucket's rec[])
     int* cursor;       // [bs][cams*L]         records allocated so far in each bucket
-    unsigned long long* sortbuf;  // [bs][cams*L][2][A*P] global ping-pong (bands that exceed shared memory)
+    unsigned long long* sortbuf;  // [bs][cams*L][2][n_ids] global ping-pong (bands that exceed shared memory)
     int4* part_list;   // [bs*num_feat + partial_cap][4]  work-list entries (kEntryInts ints), one per part item
     int4* tiny_list;   // [bs*num_feat][4]                work-list entries, one per tiny row (tiny_ok only)
     float* partial;    // [partial_cap][C]     part sums of rows with more than one part
@@ -77,6 +92,15 @@ struct GfeatParams {
     int tiny_max;      // rows with at most this many contributions go to the quarter-warp path (<= kTinyRow)
     int tiny_ok;       // shape supported by the quarter-warp kernel (C % 32 == 0, C <= 256, (C/G) % 32 == 0)
 };
+
+// call that owns sample id `sid` (ids of call k start at calls[k].id_begin; at most kMaxGfeatCalls entries)
+__device__ __forceinline__ int call_of_id(const GfeatParams& p, int sid) {
+    int k = 0;
+#pragma unroll
+    for (int i = 1; i < kMaxGfeatCalls; ++i)
+        if (i < p.ncalls && sid >= p.calls[i].id_begin) k = i;
+    return k;
+}
 
 __host__ __device__ inline int bits_for(unsigned v) {   // number of bits to represent values < v
     int b = 0;
@@ -125,7 +149,9 @@ __global__ void __launch_bounds__(kVisThreads) dfa_vis_compact_kernel(const Gfea
     const Dims d = p.d;
     const int c = blockIdx.x, cam = blockIdx.y, b_idx = blockIdx.z;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int AP = d.A * d.P;
+    const int kc = call_of_id(p, c * kVisChunk);          // a chunk belongs to exactly one call
+    const GfeatCall& gc = p.calls[kc];
+    const int AP = gc.A * gc.P;                           // samples of that call (per batch element)
     __shared__ int s_wcnt[kWarps];
     __shared__ int s_bc[kMaxCamLevels * kMaxBands];     // [level][band] counts of this chunk
 
@@ -134,14 +160,15 @@ __global__ void __launch_bounds__(kVisThreads) dfa_vis_compact_kernel(const Gfea
         if (b_idx == 0 && tid < 8) p.counters[tid] = 0;
     }
     for (int i = tid; i < d.L * kMaxBands; i += kVisThreads) s_bc[i] = 0;
-    const float2* loc2 = reinterpret_cast<const float2*>(p.loc) + (size_t)b_idx * AP * d.cams + cam;
-    const int s_base = c * kVisChunk + warp * kPerWarp;
+    const float2* loc2 = reinterpret_cast<const float2*>(gc.loc) + (size_t)b_idx * AP * d.cams + cam;
+    const int s_base = c * kVisChunk + warp * kPerWarp;   // group sample id
+    const int s_local0 = s_base - gc.id_begin;            // sample index inside the call
     float2 xy[kIter];
     unsigned bal[kIter];
     int cnt = 0;
 #pragma unroll
     for (int it = 0; it < kIter; ++it) {
-        const int s = s_base + it * 32 + lane;
+        const int s = s_local0 + it * 32 + lane;
         xy[it] = make_float2(-1.f, -1.f);
         if (s < AP) xy[it] = __ldg(loc2 + (size_t)s * d.cams);
         bal[it] = __ballot_sync(0xffffffffu, loc_valid(xy[it].x, xy[it].y));
@@ -169,7 +196,7 @@ __global__ void __launch_bounds__(kVisThreads) dfa_vis_compact_kernel(const Gfea
         if (w < warp) pos += n;
         total += n;
     }
-    const size_t list = ((size_t)b_idx * d.cams + cam) * AP + (size_t)c * kVisChunk;
+    const size_t list = ((size_t)b_idx * d.cams + cam) * p.n_ids + (size_t)c * kVisChunk;
 #pragma unroll
     for (int it = 0; it < kIter; ++it) {
         if ((bal[it] >> lane) & 1u) {
@@ -272,7 +299,7 @@ __device__ void band_sort_body(const GfeatParams& p, const BandCtx& bc, W* a, W*
                                int* seg_band) {
     const Dims d = p.d;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int AP = d.A * d.P;
+    const int AP = p.n_ids;
     const size_t cam_list = ((size_t)bc.b_idx * d.cams + bc.cam) * AP;
     const int* cnts = p.vis_cnt + ((size_t)bc.b_idx * d.cams + bc.cam) * p.n_chunks;
 
@@ -315,23 +342,39 @@ __device__ void band_sort_body(const GfeatParams& p, const BandCtx& bc, W* a, W*
 
     // sorted records: everything the reduce needs per contribution, so it never re-derives the quad
     int4* rec = p.rec + ((size_t)bc.b_idx * d.cams * d.L + bc.cl) * AP + bc.base;
-    const float2* loc2 = reinterpret_cast<const float2*>(p.loc) + (size_t)bc.b_idx * AP * d.cams + bc.cam;
+    float* recw = p.recw + (((size_t)bc.b_idx * d.cams * d.L + bc.cl) * AP + bc.base) * d.G;
+    const int lvl = bc.cl - bc.cam * d.L;
     const W vmask = ((W)1 << bc.vb) - 1;
     for (int i0 = 0; i0 < bc.n; i0 += kSortThreads * 4) {
-        int sid[4];
+        int sid[4], arow[4];
         float2 xy[4];
+        const float* wsrc[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const int i = i0 + u * kSortThreads + tid;
-            sid[u] = (i < bc.n) ? (int)(sorted[i] & vmask) : 0;
-            xy[u] = __ldg(loc2 + (size_t)sid[u] * d.cams);
+            sid[u] = (i < bc.n) ? (int)(sorted[i] & vmask) : p.calls[0].id_begin;
+            const GfeatCall& gc = p.calls[call_of_id(p, sid[u])];
+            const int s_local = sid[u] - gc.id_begin;
+            const size_t s_abs = (size_t)bc.b_idx * gc.A * gc.P + s_local;      // sample inside the call's tensors
+            xy[u] = __ldg(reinterpret_cast<const float2*>(gc.loc) + s_abs * d.cams + bc.cam);
+            wsrc[u] = gc.weights + ((s_abs * d.cams + bc.cam) * d.L + lvl) * d.G;
+            arow[u] = gc.anchor_begin + s_local / gc.P;
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const int i = i0 + u * kSortThreads + tid;
             if (i < bc.n) {
                 const Quad q = quad_setup(xy[u].x, xy[u].y, bc.h, bc.w);
-                rec[i] = make_int4(sid[u], sid[u] / d.P, __float_as_int(q.lh), __float_as_int(q.lw));
+                rec[i] = make_int4(sid[u], arow[u], __float_as_int(q.lh), __float_as_int(q.lw));
+                // the record's G weights travel with it, so the reduce reads them sequentially and never has to
+                // find the call a contribution came from
+                float* wd = recw + (size_t)i * d.G;
+                if ((d.G & 3) == 0) {
+                    for (int g = 0; g < d.G; g += 4)
+                        *reinterpret_cast<float4*>(wd + g) = __ldg(reinterpret_cast<const float4*>(wsrc[u] + g));
+                } else {
+                    for (int g = 0; g < d.G; ++g) wd[g] = __ldg(wsrc[u] + g);
+                }
             }
         }
     }
@@ -359,7 +402,7 @@ __global__ void __launch_bounds__(kSortThreads) dfa_band_sort_kernel(const Gfeat
     const int band = blockIdx.x, cl = blockIdx.y, b_idx = blockIdx.z;
     const int cam = cl / d.L;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int AP = d.A * d.P;
+    const int AP = p.n_ids;
     const int h = __ldg(p.shapes + cl * 2), w = __ldg(p.shapes + cl * 2 + 1);
     const Bands g = band_geometry(h, w, p.NB);
     if (band >= g.nb) return;
@@ -450,7 +493,7 @@ constexpr int kEntryInts = 16;   // work-list entry, shared by the part and the 
 template <int V, int NCH>
 struct RowCtx {
     const int4* rec;              // sorted records of the bucket
-    const char* wts_lane[NCH];    // weights of (b, :, :, cam, l, group of this lane's chunk j), as bytes
+    const char* wts_lane[NCH];    // record weights of the bucket at the group of this lane's chunk j, as bytes
     const char* gout_lane[NCH];   // grad_out of batch element b at this lane's channels of chunk j, as bytes
     unsigned c_bytes, w_stride_bytes;
     int beg[4];                   // begin of the corner-1/2/3/4 segments in rec[]
@@ -478,11 +521,11 @@ template <int V, int NCH>
 __device__ __forceinline__ void row_ctx_from_entry(RowCtx<V, NCH>& cx, const LaneMap<V, NCH>& lm, const GfeatParams& p,
                                                    int b_idx, int packed) {
     const Dims& d = p.d;
-    const int cam = packed & 0xff, l = (packed >> 8) & 0xff, rcl = packed >> 16;
-    const size_t AP = (size_t)d.A * d.P;
+    const int rcl = packed >> 16;
+    const size_t AP = (size_t)p.n_ids;
     cx.rec = p.rec + ((size_t)b_idx * d.cams * d.L + rcl) * AP;
-    const float* wts = p.weights + (((size_t)b_idx * AP * d.cams + cam) * d.L + l) * d.G;
-    const float* gout = p.grad_out + (size_t)b_idx * d.A * d.C;
+    const float* wts = p.recw + ((size_t)b_idx * d.cams * d.L + rcl) * AP * d.G;
+    const float* gout = p.grad_out + (size_t)b_idx * p.A_total * d.C;
 #pragma unroll
     for (int j = 0; j < NCH; ++j) {
         cx.wts_lane[j] = reinterpret_cast<const char*>(wts + lm.grp[j]);
@@ -509,13 +552,14 @@ __device__ __forceinline__ void accumulate_row(const RowCtx<V, NCH>& cx, int c_l
         const int k = (v >= cx.e1) + (v >= cx.e2) + (v >= cx.e3);
         const int first = (k == 0) ? 0 : (k == 1) ? cx.e1 : (k == 2) ? cx.e2 : cx.e3;
         const int bk = (k == 0) ? cx.beg[0] : (k == 1) ? cx.beg[1] : (k == 2) ? cx.beg[2] : cx.beg[3];
-        const int4 e = __ldg(cx.rec + bk + (v - first));
+        const int pos = bk + (v - first);                             // record index inside the bucket
+        const int4 e = __ldg(cx.rec + pos);
         const float lh = __int_as_float(e.z), lw = __int_as_float(e.w);
         const float hh = 1.f - lh, hw = 1.f - lw;    // same expressions as quad_setup()
         float coef = (k == 0) ? hh * hw : (k == 1) ? hh * lw : (k == 2) ? lh * hw : lh * lw;
         if (v0 + lane >= c_hi) coef = 0.f;
         const unsigned go_off = (unsigned)e.y * cx.c_bytes;           // < 2^32 checked on the host
-        const unsigned w_off = (unsigned)e.x * cx.w_stride_bytes;
+        const unsigned w_off = (unsigned)pos * cx.w_stride_bytes;
         const int cnt = min(32, c_hi - v0);
         for (int m0 = 0; m0 < cnt; m0 += kReduceBatch) {
             float g[kReduceBatch][NCH][V];
@@ -660,13 +704,13 @@ __global__ void __launch_bounds__(256, 2) dfa_gfeat_reduce_kernel(const GfeatPar
     const int n_tiny = (NQ > 0) ? p.counters[3] : 0;
     const int total = n_parts + (n_tiny + 3) / 4;
     const int n_cl = d.cams * d.L;
-    const size_t AP = (size_t)d.A * d.P;
+    const size_t AP = (size_t)p.n_ids;
 
     LaneMap<V, NCH> lm;
     lm.init(d.C, d.G);
     RowCtx<V, NCH> cx;
     cx.c_bytes = (unsigned)d.C * 4u;
-    cx.w_stride_bytes = (unsigned)(n_cl * d.G) * 4u;
+    cx.w_stride_bytes = (unsigned)d.G * 4u;       // one record's weights
     const int* plist = reinterpret_cast<const int*>(p.part_list);
     const int* tlist = reinterpret_cast<const int*>(p.tiny_list);
 
@@ -806,11 +850,10 @@ __global__ void __launch_bounds__(256, 2) dfa_gfeat_reduce_kernel(const GfeatPar
             const int b3 = __shfl_sync(0xffffffffu, fa, 6, 8), b4 = __shfl_sync(0xffffffffu, fa, 7, 8);
             const int e1 = __shfl_sync(0xffffffffu, fb, 0, 8), e2 = __shfl_sync(0xffffffffu, fb, 1, 8);
             const int e3 = __shfl_sync(0xffffffffu, fb, 2, 8);
-            const int cam = packed & 0xff, l = (packed >> 8) & 0xff, rcl = packed >> 16;
+            const int rcl = packed >> 16;
             const int4* rec = p.rec + ((size_t)b_idx * n_cl + rcl) * AP;
-            const char* wts =
-                reinterpret_cast<const char*>(p.weights + (((size_t)b_idx * AP * d.cams + cam) * d.L + l) * d.G);
-            const char* gout = reinterpret_cast<const char*>(p.grad_out + (size_t)b_idx * d.A * d.C + sub * 4);
+            const char* wts = reinterpret_cast<const char*>(p.recw + ((size_t)b_idx * n_cl + rcl) * AP * d.G);
+            const char* gout = reinterpret_cast<const char*>(p.grad_out + (size_t)b_idx * p.A_total * d.C + sub * 4);
             const int gd = d.C / d.G;
 
             // lane `sub` holds contribution `sub` of its quarter's row (clamped onto the last one, coefficient 0)
@@ -821,13 +864,14 @@ __global__ void __launch_bounds__(256, 2) dfa_gfeat_reduce_kernel(const GfeatPar
                 const int k = (v >= e1) + (v >= e2) + (v >= e3);
                 const int first = (k == 0) ? 0 : (k == 1) ? e1 : (k == 2) ? e2 : e3;
                 const int bk = (k == 0) ? b1 : (k == 1) ? b2 : (k == 2) ? b3 : b4;
-                const int4 e = __ldg(rec + bk + (v - first));
+                const int pos = bk + (v - first);
+                const int4 e = __ldg(rec + pos);
                 const float lh = __int_as_float(e.z), lw = __int_as_float(e.w);
                 const float hh = 1.f - lh, hw = 1.f - lw;    // same expressions as quad_setup()
                 coef = (k == 0) ? hh * hw : (k == 1) ? hh * lw : (k == 2) ? lh * hw : lh * lw;
                 if (sub >= n) coef = 0.f;
                 go_off = (unsigned)e.y * cx.c_bytes;
-                w_off = (unsigned)e.x * cx.w_stride_bytes;
+                w_off = (unsigned)pos * cx.w_stride_bytes;
             }
             const int n_max = __reduce_max_sync(0xffffffffu, n);
             constexpr int NQ1 = (NQ > 0) ? NQ : 1;

@@ -1,0 +1,161 @@
+// dfa_group.cu — host side of the grouped sample-major kernel (dfa_group.cuh): unit planning, forward launcher,
+// and the sample-major half of the grouped backward (called from dfa_backward.cu).
+#include "dfa_dispatch.cuh"
+#include "dfa_group.cuh"
+#include "dfa_group_host.h"
+
+namespace hipad {
+
+namespace {
+constexpr size_t kAlignG = 256;
+inline size_t align_g(size_t v) { return (v + kAlignG - 1) / kAlignG * kAlignG; }
+
+inline int group_warps() {
+    const int w = hipad_env_int("HIPAD_DFA_GROUP_WARPS", 4);
+    return (w == 8) ? 8 : 4;
+}
+// (p,cam) pairs per unit: the forward keeps whole det rows (78 pairs) in one unit; the backward's metadata is
+// larger per pair (shared memory per CTA decides how many CTAs an SM holds), so its units are half as long
+inline int group_ps_max(bool bwd) {
+    const int dflt = bwd ? 64 : 128;
+    const int v = hipad_env_int(bwd ? "HIPAD_DFA_GROUP_PS_BWD" : "HIPAD_DFA_GROUP_PS_FWD", dflt);
+    return (v >= 16 && v <= kGroupMaxPS) ? v : dflt;
+}
+
+template <typename T, int V, int NCH, bool kBwd, int kW>
+int launch_inst(const GroupParams& gp, int grid, size_t smem, cudaStream_t st) {
+    auto kern = dfa_group_kernel<T, V, NCH, kBwd, kW>;
+    cudaError_t e = ensure_smem(kern, smem);
+    if (e != cudaSuccess) return (int)e;
+    kern<<<grid, kW * 32, smem, st>>>(gp);
+    return (int)cudaGetLastError();
+}
+
+template <bool kBwd, int kW>
+int dispatch(ElemType t, const GroupParams& gp, int grid, size_t smem, cudaStream_t st) {
+    if (t == kF32) {
+        if (gp.C == 128) return launch_inst<float, 4, 1, kBwd, kW>(gp, grid, smem, st);
+        if (gp.C == 256) return launch_inst<float, 4, 2, kBwd, kW>(gp, grid, smem, st);
+    } else {
+        if (gp.C == 256) return launch_inst<__nv_bfloat16, 8, 1, kBwd, kW>(gp, grid, smem, st);
+    }
+    return -2;
+}
+}  // namespace
+
+bool group_kernel_supported(ElemType t, int C, int L, int G, int cams) {
+    if (hipad_env_int("HIPAD_DFA_GROUP_KERNEL", 1) == 0) return false;      // A/B knob: round-1 kernels only
+    if (L != kGroupL || G < 1 || G > kGroupMaxG || C % G != 0 || cams * L > kMaxCamLevels) return false;
+    const int V = (t == kF32) ? 4 : 8;
+    const int gd = C / G;
+    if (gd % V != 0) return false;
+    const int lpg = gd / V;
+    if (lpg > 32 || (lpg & (lpg - 1)) != 0) return false;
+    if (t == kF32) return C == 128 || C == 256;
+    return C == 256;
+}
+
+GroupPlan plan_group(bool bwd, const CallDesc* calls, int ncalls, int bs, int cams, int C, int forced_single_slice) {
+    GroupPlan pl = {};
+    const int ps_cap = group_ps_max(bwd);
+    long long units = 0, parts = 0, rows = 0;
+    int ps_max = 16;
+    for (int k = 0; k < ncalls; ++k) {
+        const int NP = calls[k].P * cams;
+        int S = forced_single_slice ? 1 : (NP + ps_cap - 1) / ps_cap;
+        if (S < 1) S = 1;
+        const int PS = (NP + S - 1) / S;
+        S = (NP + PS - 1) / PS;                       // no empty slice
+        pl.S[k] = S;
+        pl.PS[k] = PS;
+        pl.unit_begin[k] = units;
+        units += (long long)bs * calls[k].A * S;
+        if (!bwd && S > 1) {
+            pl.part_begin[k] = parts;
+            pl.row_begin[k] = rows;
+            parts += (long long)bs * calls[k].A * S;
+            rows += (long long)bs * calls[k].A;
+        }
+        if (PS > ps_max) ps_max = PS;
+    }
+    pl.units = units;
+    pl.parts = parts;
+    pl.rows = rows;
+    pl.ps_max = ps_max;
+    pl.partial_bytes = align_g((size_t)parts * C * sizeof(float));
+    pl.ticket_bytes = align_g((size_t)rows * sizeof(int));
+    return pl;
+}
+
+size_t group_forward_workspace_bytes(const CallDesc* calls, int ncalls, int bs, int cams, int C) {
+    if (ncalls < 1 || ncalls > kMaxCalls) return 0;
+    const GroupPlan pl = plan_group(false, calls, ncalls, bs, cams, C, 0);
+    return pl.partial_bytes + pl.ticket_bytes + kAlignG;
+}
+
+// fills the call table shared by the forward and backward launches; returns 0 or an error
+int fill_group_params(GroupParams& gp, const GroupPlan& pl, const CallDesc* calls, int ncalls, int bs, int cams,
+                      int num_feat, int C, int G, long long io_bstride, float* out, const float* grad_out) {
+    if (pl.units <= 0 || pl.units > 0x7fffffffLL) return -2;
+    gp.ncalls = ncalls; gp.bs = bs; gp.cams = cams; gp.num_feat = num_feat; gp.C = C; gp.G = G;
+    gp.ps_max = pl.ps_max;
+    long long a_begin = 0;
+    for (int k = 0; k < ncalls; ++k) {
+        GroupCall& c = gp.calls[k];
+        c.loc = calls[k].loc; c.weights = calls[k].weights; c.g_loc = calls[k].g_loc; c.g_w = calls[k].g_w;
+        c.out = out ? out + a_begin * C : nullptr;
+        c.grad_out = grad_out ? grad_out + a_begin * C : nullptr;
+        c.io_bstride = io_bstride;
+        c.A = calls[k].A; c.P = calls[k].P; c.S = pl.S[k]; c.PS = pl.PS[k];
+        c.unit_begin = (int)pl.unit_begin[k];
+        c.part_begin = (int)pl.part_begin[k];
+        c.row_begin = (int)pl.row_begin[k];
+        a_begin += calls[k].A;
+        // 32-bit element offsets inside one call's tensors are not assumed anywhere; pair counts are ints
+        if ((long long)calls[k].P * cams > (1 << 24)) return -2;
+    }
+    return 0;
+}
+
+int launch_group_sample(bool bwd, ElemType t, const GroupParams& gp, long long units, cudaStream_t st) {
+    const int kw = group_warps();
+    const int V = (t == kF32) ? 4 : 8;
+    const int nch = gp.C / (32 * V);
+    GroupParams g = gp;
+    g.so = group_smem_layout(bwd, gp.ps_max, nch * 32 * V, kw);
+    const size_t smem = (size_t)g.so.total;
+    if (smem > kSampleSmemBudget) return -2;
+    if (bwd) return kw == 8 ? dispatch<true, 8>(t, g, (int)units, smem, st) : dispatch<true, 4>(t, g, (int)units, smem, st);
+    return kw == 8 ? dispatch<false, 8>(t, g, (int)units, smem, st) : dispatch<false, 4>(t, g, (int)units, smem, st);
+}
+
+int launch_group_forward(const GroupFwdArgs& a) {
+    if (a.ncalls < 1 || a.ncalls > kMaxCalls) return -1;
+    if (!group_kernel_supported(a.type, a.C, a.L, a.G, a.cams)) return -2;
+    if ((long long)a.num_feat * a.C >= (1LL << 30)) return -2;
+    if (reinterpret_cast<uintptr_t>(a.feat) % 16 != 0 || reinterpret_cast<uintptr_t>(a.out) % 16 != 0) return -2;
+    for (int k = 0; k < a.ncalls; ++k)
+        if (reinterpret_cast<uintptr_t>(a.calls[k].loc) % 8 != 0 || reinterpret_cast<uintptr_t>(a.calls[k].weights) % 16 != 0)
+            return -2;
+    const bool no_ws = a.workspace == nullptr;
+    const GroupPlan pl = plan_group(false, a.calls, a.ncalls, a.bs, a.cams, a.C, no_ws ? 1 : 0);
+    if (pl.ps_max > kGroupMaxPS) return -2;             // (only reachable without a workspace: rows cannot be sliced)
+    GroupParams gp = {};
+    gp.feat = a.feat; gp.shapes = a.shapes; gp.starts = a.starts;
+    long long a_total = 0;
+    for (int k = 0; k < a.ncalls; ++k) a_total += a.calls[k].A;
+    int rc = fill_group_params(gp, pl, a.calls, a.ncalls, a.bs, a.cams, a.num_feat, a.C, a.G, a_total * a.C, a.out, nullptr);
+    if (rc != 0) return rc;
+    if (pl.parts > 0) {
+        if (reinterpret_cast<uintptr_t>(a.workspace) % kAlignG != 0 ||
+            a.workspace_bytes < pl.partial_bytes + pl.ticket_bytes)
+            return -3;
+        gp.partial = reinterpret_cast<float*>(a.workspace);
+        gp.tickets = reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(a.workspace) + pl.partial_bytes);
+        const cudaError_t e = cudaMemsetAsync(gp.tickets, 0, (size_t)pl.rows * sizeof(int), a.stream);
+        if (e != cudaSuccess) return (int)e;
+    }
+    return launch_group_sample(false, a.type, gp, pl.units, a.stream);
+}
+
+}  // namespace hipad

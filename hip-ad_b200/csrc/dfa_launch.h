@@ -65,6 +65,56 @@ int launch_backward(const BwdArgs& a);
 size_t backward_workspace_bytes(const Dims& d);
 size_t backward_counters_offset(const Dims& d);   // debugging: where the 8 work counters live in the workspace
 
+// ---- grouped launches: several aggregation calls that read the same feature maps (one decoder layer) -------------
+constexpr int kMaxCalls = 8;
+struct CallDesc {
+    const float* loc;        // [bs, A, P, cams, 2]
+    const float* weights;    // [bs, A, P, cams, L, G]
+    float* g_loc;            // backward only
+    float* g_w;              // backward only
+    int A, P;
+};
+struct GroupFwdArgs {
+    ElemType type;
+    float* out;              // packed [bs, A_total, C]: call k owns rows [a_begin_k, a_begin_k + A_k) of every batch element
+    const void* feat;
+    const int* shapes;
+    const int* starts;
+    CallDesc calls[kMaxCalls];
+    int ncalls;
+    int bs, cams, num_feat, C, L, G;
+    void* workspace;         // partial rows + tickets of sliced rows (group_forward_workspace_bytes)
+    size_t workspace_bytes;
+    cudaStream_t stream;
+};
+int launch_group_forward(const GroupFwdArgs& a);
+size_t group_forward_workspace_bytes(const CallDesc* calls, int ncalls, int bs, int cams, int C);
+// true when the grouped sample kernel (dfa_group.cuh) covers this layout; otherwise callers use the per-call kernels
+bool group_kernel_supported(ElemType t, int C, int L, int G, int cams);
+
+struct GroupBwdArgs {
+    ElemType type;
+    const void* feat;
+    const int* shapes;
+    const int* starts;
+    CallDesc calls[kMaxCalls];
+    int ncalls;
+    const float* grad_out;   // packed [bs, A_total, C]
+    void* g_feat;            // [bs, num_feat, C] or null (frozen features)
+    bool g_feat_f32;         // g_feat is fp32 whatever the feature type (shared accumulation buffer)
+    bool accumulate;         // g_feat += instead of zero fill + overwrite
+    int bs, cams, num_feat, C, L, G;
+    void* workspace;
+    size_t workspace_bytes;
+    cudaStream_t stream;
+    int stage_mask;          // bit0 sample-major kernel (+ zero fill), bit1 compaction + sort, bit2 classify + reduce
+    bool classify_only;
+    bool separate_zero_fill;
+};
+int launch_group_backward(const GroupBwdArgs& a);
+size_t group_backward_workspace_bytes(const CallDesc* calls, int ncalls, int bs, int cams, int num_feat, int C, int L, int G);
+size_t group_backward_counters_offset(const CallDesc* calls, int ncalls, int bs, int cams, int num_feat, int C, int L, int G);
+
 int launch_indices(int32_t* idx, const int* shapes, const int* starts, const float* loc, int bs, int cams, int L,
                    int A, int P, cudaStream_t stream);
 

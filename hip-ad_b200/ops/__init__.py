@@ -10,7 +10,10 @@ import torch
 from .deformable_aggregation import (  # noqa: F401
     DeformableAggregationFunction,
     DeformableAggregationFunctionA800,
+    DeformableAggregationGroupFunction,
     FeatureMapsFormatFunction,
+    KernelTimer,
+    deformable_aggregation_group,
     format_feature_levels,
     fused_deformable_aggregation,
     sample_indices,

@@ -22,6 +22,48 @@ from torch.autograd.function import Function, once_differentiable
 from .. import _lib
 
 
+_ACTIVE_TIMER = None
+
+
+class KernelTimer:
+    """Measurement aid: ``with KernelTimer() as t:`` puts CUDA events (current stream) around every launch sequence
+    this package issues inside the block; ``t.summary()`` -> {"forward": ms, "backward": ms}.  Off by default."""
+
+    def __init__(self):
+        self.spans = {"forward": [], "backward": []}
+        self._prev = None
+
+    def __enter__(self):
+        global _ACTIVE_TIMER
+        self._prev, _ACTIVE_TIMER = _ACTIVE_TIMER, self
+        return self
+
+    def __exit__(self, *exc):
+        global _ACTIVE_TIMER
+        _ACTIVE_TIMER = self._prev
+
+    def summary(self):
+        torch.cuda.synchronize()
+        return {k: float(sum(a.elapsed_time(b) for a, b in v)) for k, v in self.spans.items()}
+
+
+class _timed:
+    def __init__(self, kind):
+        self.kind = kind
+        self.t = _ACTIVE_TIMER
+
+    def __enter__(self):
+        if self.t is not None:
+            self.a = torch.cuda.Event(enable_timing=True)
+            self.a.record()
+
+    def __exit__(self, *exc):
+        if self.t is not None:
+            b = torch.cuda.Event(enable_timing=True)
+            b.record()
+            self.t.spans[self.kind].append((self.a, b))
+
+
 def _as_i32(t):
     cached = getattr(t, "_hipad_i32", None)
     if cached is not None and cached.device == t.device:
@@ -55,17 +97,50 @@ def _norm_feat(feat):
 
 
 class _GradHolder:
-    """One dense feature-gradient buffer shared by every aggregation call that reads the same feature tensor."""
-    __slots__ = ("buffer",)
+    """One dense feature-gradient buffer shared by every aggregation call that reads the same feature tensor.
+    The buffer belongs to ONE backward pass (``task``: the autograd graph-task id that created it): a pass that
+    never reaches the sink node (``autograd.grad`` w.r.t. locations only, an exception, a partial graph under
+    ``retain_graph``) must not leave a stale buffer for the next one."""
+    __slots__ = ("buffer", "task")
 
     def __init__(self):
         self.buffer = None
+        self.task = None
+
+
+def _current_task():
+    try:
+        return torch._C._current_graph_task_id()
+    except Exception:
+        return -1
+
+
+def _holder_buffer(holder):
+    """The shared buffer of the CURRENT backward pass, or None (a buffer left by another pass is dropped)."""
+    if holder.buffer is not None and holder.task != _current_task():
+        holder.buffer = None
+    return holder.buffer
+
+
+def _holder_publish(holder, buffer):
+    if holder.buffer is None:
+        holder.task = _current_task()
+
+        def _end_of_pass(h=holder, t=holder.task):
+            if h.task == t:            # the sink did not run in this pass: nobody will read the buffer
+                h.buffer = None
+        try:
+            torch.autograd.Variable._execution_engine.queue_callback(_end_of_pass)
+        except Exception:
+            pass
+    holder.buffer = buffer
 
 
 class _SharedFeatureGradient(Function):
-    """Identity on the feature tensor.  The aggregation calls downstream add their feature gradients into ONE buffer
-    (hipad_dfa_backward_accumulate_*) and return no gradient of their own; this node hands the buffer to autograd
-    once, after all of them have run (autograd's topological order guarantees that)."""
+    """Identity on the feature tensor.  The aggregation calls downstream add their feature gradients into ONE fp32
+    buffer (hipad_dfa_group_backward with the accumulate flag) and return no gradient of their own; this node hands
+    the buffer to autograd once, after all of them have run (autograd's topological order guarantees that), narrowed
+    to the feature dtype in one rounding."""
 
     @staticmethod
     def forward(ctx, feat, holder):
@@ -77,8 +152,9 @@ class _SharedFeatureGradient(Function):
     @staticmethod
     @once_differentiable
     def backward(ctx, grad):
-        shared = ctx.holder.buffer
+        shared = _holder_buffer(ctx.holder)
         ctx.holder.buffer = None
+        ctx.holder.task = None
         if shared is None:
             return grad, None
         if grad is not None:           # consumers that are not aggregation calls (e.g. the inverse-format views)
@@ -87,16 +163,76 @@ class _SharedFeatureGradient(Function):
 
 
 def share_feature_gradient(col_feats):
-    """Returns ``col_feats`` wired so that all ``deformable_aggregation_function`` calls consuming the RETURNED tensor
-    accumulate their feature gradients into one dense buffer: one zero fill and no per-call dense gradient
-    (the reference materialises and autograd sums one [bs, F, C] tensor per call, 24 per stage-2 step).
-    Results are identical up to fp32 summation order, which stays deterministic (backward call order)."""
+    """Returns ``col_feats`` wired so that all ``deformable_aggregation_function`` / ``deformable_aggregation_group``
+    calls consuming the RETURNED tensor accumulate their feature gradients into one dense fp32 buffer: one zero fill
+    per step and no per-call dense gradient (the reference materialises and autograd sums one [bs, F, C] tensor per
+    call, 24 per stage-2 step).  Results are identical up to fp32 summation order, which stays deterministic
+    (backward call order)."""
     if not (torch.is_tensor(col_feats) and col_feats.is_cuda and col_feats.requires_grad):
         return col_feats
     holder = _GradHolder()
     out = _SharedFeatureGradient.apply(col_feats, holder)
     out._hipad_gsink = holder
     return out
+
+
+def _group_dims(feat, shapes, G):
+    bs, num_feat, C = feat.shape
+    cams, L = shapes.shape[:2]
+    return bs, cams, num_feat, C, L, G
+
+
+def _run_group_forward(lib, feat, shapes, starts, locs, ws_, out):
+    """One launch for all (loc, weights) pairs.  Returns the status (ERR_UNSUPPORTED: caller goes call by call)."""
+    bs, num_feat, C = feat.shape
+    cams, L = shapes.shape[:2]
+    G = ws_[0].shape[-1]
+    table = _lib.call_table([(l.data_ptr(), w.data_ptr(), None, None, l.shape[1], l.shape[2]) for l, w in zip(locs, ws_)])
+    import ctypes
+    tp = ctypes.cast(table, ctypes.c_void_p)
+    nbytes = lib.hipad_dfa_group_forward_workspace_bytes(tp, len(locs), bs, cams, C)
+    work = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=feat.device)
+    with _timed("forward"):
+        return lib.hipad_dfa_group_forward(1 if feat.dtype == torch.bfloat16 else 0, out.data_ptr(), feat.data_ptr(),
+                                           shapes.data_ptr(), starts.data_ptr(), tp, len(locs), bs, cams, num_feat, C, L, G,
+                                           work.data_ptr(), work.numel(), torch.cuda.current_stream().cuda_stream)
+
+
+def _run_group_backward(lib, feat, shapes, starts, locs, ws_, go_packed, need_feat, holder):
+    """One backward chain for all calls.  Returns (status, g_feat or None, [g_loc], [g_w]); with a holder the feature
+    gradient is accumulated into the pass-wide fp32 buffer and g_feat is None."""
+    import ctypes
+    bs, num_feat, C = feat.shape
+    cams, L = shapes.shape[:2]
+    G = ws_[0].shape[-1]
+    bf16 = feat.dtype == torch.bfloat16
+    g_locs = [torch.empty_like(l) for l in locs]
+    g_ws = [torch.empty_like(w) for w in ws_]
+    flags, g_feat = 0, None
+    if need_feat:
+        shared = _holder_buffer(holder) if holder is not None else None
+        if holder is not None:
+            flags |= 2                                   # shared buffers are fp32 whatever the feature type
+            if shared is not None:
+                g_feat, flags = shared, flags | 1
+            else:
+                g_feat = torch.empty(feat.shape, dtype=torch.float32, device=feat.device)
+        else:
+            g_feat = torch.empty_like(feat)
+    table = _lib.call_table([(l.data_ptr(), w.data_ptr(), gl.data_ptr(), gw.data_ptr(), l.shape[1], l.shape[2])
+                             for l, w, gl, gw in zip(locs, ws_, g_locs, g_ws)])
+    tp = ctypes.cast(table, ctypes.c_void_p)
+    nbytes = lib.hipad_dfa_group_backward_workspace_bytes(tp, len(locs), bs, cams, num_feat, C, L, G) if need_feat else 0
+    work = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=feat.device)
+    with _timed("backward"):
+        rc = lib.hipad_dfa_group_backward(1 if bf16 else 0, flags, feat.data_ptr(), shapes.data_ptr(), starts.data_ptr(),
+                                          tp, len(locs), go_packed.data_ptr(), g_feat.data_ptr() if need_feat else None,
+                                          bs, cams, num_feat, C, L, G, work.data_ptr(), work.numel(),
+                                          torch.cuda.current_stream().cuda_stream)
+    if rc == 0 and need_feat and holder is not None:
+        _holder_publish(holder, g_feat)
+        g_feat = None
+    return rc, g_feat, g_locs, g_ws
 
 
 class DeformableAggregationFunction(Function):
@@ -111,13 +247,17 @@ class DeformableAggregationFunction(Function):
         loc = sampling_location.contiguous().float()
         w = weights.contiguous().float()
         dims = _dims(feat, shapes, loc, w)
-        bs, _, _, C, _, A, _, _ = dims
+        bs, _, _, C, L, A, P, G = dims
+        w = w.view(bs, A, P, dims[1], L, G)
         with torch.cuda.device(feat.device):
             out = torch.empty((bs, A, C), dtype=torch.float32, device=feat.device)
-            stream = torch.cuda.current_stream().cuda_stream
-            fn = lib.hipad_dfa_forward_bf16 if feat.dtype == torch.bfloat16 else lib.hipad_dfa_forward_f32
-            rc = fn(out.data_ptr(), feat.data_ptr(), shapes.data_ptr(), starts.data_ptr(),
-                    loc.data_ptr(), w.data_ptr(), *dims, stream)
+            # grouped kernel with a single call (rows of map / plan queries are cut into work units, which needs the
+            # workspace this entry point takes); layouts it does not cover run on the 5-argument entry point
+            rc = _run_group_forward(lib, feat, shapes, starts, [loc], [w], out)
+            if rc == _lib.ERR_UNSUPPORTED:
+                fn = lib.hipad_dfa_forward_bf16 if feat.dtype == torch.bfloat16 else lib.hipad_dfa_forward_f32
+                rc = fn(out.data_ptr(), feat.data_ptr(), shapes.data_ptr(), starts.data_ptr(),
+                        loc.data_ptr(), w.data_ptr(), *dims, torch.cuda.current_stream().cuda_stream)
         _lib.check(rc, "hipad_dfa_forward")
         ctx.save_for_backward(feat, shapes, starts, loc, w)
         ctx.feat_dtype = mc_ms_feat.dtype
@@ -128,36 +268,95 @@ class DeformableAggregationFunction(Function):
     def backward(ctx, grad_output):
         lib = _lib.get()
         feat, shapes, starts, loc, w = ctx.saved_tensors
-        dims = _dims(feat, shapes, loc, w)
         need_feat = ctx.needs_input_grad[0]
         go = grad_output.contiguous().float()
         holder = ctx.gsink if need_feat else None
-        accumulate = holder is not None and holder.buffer is not None
-        bf16 = feat.dtype == torch.bfloat16
         with torch.cuda.device(feat.device):
-            if accumulate:
-                g_feat = holder.buffer
-            else:
-                g_feat = torch.empty_like(feat) if need_feat else None
-            g_loc = torch.empty_like(loc)
-            g_w = torch.empty_like(w)
-            nbytes = lib.hipad_dfa_backward_workspace_bytes(*dims)
-            ws = torch.empty(nbytes, dtype=torch.uint8, device=feat.device)
-            stream = torch.cuda.current_stream().cuda_stream
-            if accumulate:
-                fn = lib.hipad_dfa_backward_accumulate_bf16 if bf16 else lib.hipad_dfa_backward_accumulate_f32
-            else:
-                fn = lib.hipad_dfa_backward_bf16 if bf16 else lib.hipad_dfa_backward_f32
-            rc = fn(feat.data_ptr(), shapes.data_ptr(), starts.data_ptr(), loc.data_ptr(), w.data_ptr(),
-                    go.data_ptr(), g_feat.data_ptr() if need_feat else None, g_loc.data_ptr(), g_w.data_ptr(),
-                    *dims, ws.data_ptr(), nbytes, stream)
+            rc, g_feat, g_locs, g_ws = _run_group_backward(lib, feat, shapes, starts, [loc], [w], go, need_feat, holder)
         _lib.check(rc, "hipad_dfa_backward")
-        if holder is not None:         # the shared buffer is handed to autograd by _SharedFeatureGradient
-            holder.buffer = g_feat
-            return None, None, None, g_loc, g_w
-        if need_feat and g_feat.dtype != ctx.feat_dtype:
+        if need_feat and g_feat is not None and g_feat.dtype != ctx.feat_dtype:
             g_feat = g_feat.to(ctx.feat_dtype)
-        return g_feat, None, None, g_loc, g_w
+        return g_feat, None, None, g_locs[0], g_ws[0]
+
+
+class DeformableAggregationGroupFunction(Function):
+    """All aggregation calls of one decoder layer (they read the same feature maps) as ONE forward launch and ONE
+    backward chain with ONE feature gradient.  apply(feat, shapes, starts, loc_0, w_0, loc_1, w_1, ...) returns the
+    packed output [bs, sum(A_k), C]; ``deformable_aggregation_group`` splits it per call."""
+
+    @staticmethod
+    def forward(ctx, mc_ms_feat, spatial_shape, scale_start_index, *loc_w):
+        lib = _lib.get()
+        ctx.gsink = getattr(mc_ms_feat, "_hipad_gsink", None)
+        _require_cuda(mc_ms_feat, spatial_shape, scale_start_index, *loc_w)
+        feat = _norm_feat(mc_ms_feat)
+        shapes = _as_i32(spatial_shape)
+        starts = _as_i32(scale_start_index)
+        locs = [t.contiguous().float() for t in loc_w[0::2]]
+        ws_ = []
+        for l, w in zip(locs, loc_w[1::2]):
+            w = w.contiguous().float()
+            d = _dims(feat, shapes, l, w)
+            ws_.append(w.view(d[0], d[5], d[6], d[1], d[4], d[7]))
+        bs, _, C = feat.shape
+        a_total = sum(l.shape[1] for l in locs)
+        with torch.cuda.device(feat.device):
+            out = torch.empty((bs, a_total, C), dtype=torch.float32, device=feat.device)
+            rc = _run_group_forward(lib, feat, shapes, starts, locs, ws_, out)
+        _lib.check(rc, "hipad_dfa_group_forward")
+        ctx.save_for_backward(feat, shapes, starts, *locs, *ws_)
+        ctx.n = len(locs)
+        ctx.feat_dtype = mc_ms_feat.dtype
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_output):
+        lib = _lib.get()
+        feat, shapes, starts = ctx.saved_tensors[:3]
+        locs = list(ctx.saved_tensors[3:3 + ctx.n])
+        ws_ = list(ctx.saved_tensors[3 + ctx.n:])
+        need_feat = ctx.needs_input_grad[0]
+        go = grad_output.contiguous().float()
+        holder = ctx.gsink if need_feat else None
+        with torch.cuda.device(feat.device):
+            rc, g_feat, g_locs, g_ws = _run_group_backward(lib, feat, shapes, starts, locs, ws_, go, need_feat, holder)
+        _lib.check(rc, "hipad_dfa_group_backward")
+        if need_feat and g_feat is not None and g_feat.dtype != ctx.feat_dtype:
+            g_feat = g_feat.to(ctx.feat_dtype)
+        flat = []
+        for gl, gw in zip(g_locs, g_ws):
+            flat += [gl, gw]
+        return (g_feat, None, None, *flat)
+
+
+def group_supported(mc_ms_feat, spatial_shape, weights_list):
+    """True when the grouped kernels cover this layout (4 levels, <= 8 groups, C = 128/256 f32 or 256 bf16)."""
+    C = mc_ms_feat.shape[-1]
+    L = spatial_shape.shape[1]
+    G = weights_list[0].shape[-1]
+    if L != 4 or G > 8 or C % G != 0 or any(w.shape[-1] != G for w in weights_list):
+        return False
+    if mc_ms_feat.dtype == torch.bfloat16:
+        return C == 256 and (C // G) % 8 == 0
+    return C in (128, 256) and (C // G) % 4 == 0
+
+
+def deformable_aggregation_group(mc_ms_feat, spatial_shape, scale_start_index, calls):
+    """calls: list of (sampling_location [bs,A_k,P_k,cams,2], weights [bs,A_k,P_k,cams,L,G]) reading the SAME feature
+    maps (the det / map / plan / ego calls of one decoder layer, sparse_onedecoder.py:867-887).  Returns the list of
+    outputs [bs,A_k,C], computed by one launch (and differentiated by one backward chain writing one feature
+    gradient).  Layouts outside the grouped kernels' family are run call by call: same results."""
+    calls = list(calls)
+    if not calls:
+        return []
+    if len(calls) > _lib.MAX_GROUP_CALLS or not group_supported(mc_ms_feat, spatial_shape, [w for _, w in calls]):
+        return [DeformableAggregationFunction.apply(mc_ms_feat, spatial_shape, scale_start_index, l, w) for l, w in calls]
+    flat = []
+    for l, w in calls:
+        flat += [l, w]
+    packed = DeformableAggregationGroupFunction.apply(mc_ms_feat, spatial_shape, scale_start_index, *flat)
+    return list(packed.split([l.shape[1] for l, _ in calls], dim=1))
 
 
 # import-compatibility alias (ops/__init__.py:3-4 of the reference exports both names; the A800
@@ -197,9 +396,10 @@ def fused_deformable_aggregation(feature_maps, key_points, projection_mat, image
         loc = torch.empty((bs, A, P, cams, 2), dtype=torch.float32, device=feat.device) if return_locations else None
         stream = torch.cuda.current_stream().cuda_stream
         fn = lib.hipad_dfa_fused_forward_bf16 if feat.dtype == torch.bfloat16 else lib.hipad_dfa_fused_forward_f32
-        rc = fn(out.data_ptr(), feat.data_ptr(), shapes.data_ptr(), starts.data_ptr(), kp.data_ptr(), pm.data_ptr(),
-                wh.data_ptr() if wh is not None else None, lg.data_ptr(),
-                loc.data_ptr() if loc is not None else None, *dims, stream)
+        with _timed("forward"):
+            rc = fn(out.data_ptr(), feat.data_ptr(), shapes.data_ptr(), starts.data_ptr(), kp.data_ptr(), pm.data_ptr(),
+                    wh.data_ptr() if wh is not None else None, lg.data_ptr(),
+                    loc.data_ptr() if loc is not None else None, *dims, stream)
     _lib.check(rc, "hipad_dfa_fused_forward")
     return (out, loc) if return_locations else out
 

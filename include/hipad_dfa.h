@@ -5,9 +5,11 @@
  * plain device pointers + sizes + a CUDA stream and returns an int status
  * (0 = success, >0 = cudaError_t value, <0 = HIPAD_DFA_ERR_*).  No torch types,
  * no hidden device allocation: the caller owns every buffer,
- * including the backward workspace.  All launches go to the given stream (the
+ * including the workspaces.  All launches go to the given stream (the
  * backward additionally forks part of its work onto one helper stream per caller
- * stream, created on first use and joined before the call's last kernel) and are
+ * stream, created on first use, joined before the call returns on every path, and kept for the life of
+ * the process: the only process-wide state; a caller stream must be driven by one host thread at a time,
+ * and cudaStreamPerThread callers run the backward without the helper) and are
  * CUDA-graph capturable (no host synchronisation, no legacy-stream use).
  *
  * Reference interfaces replaced (paths relative to the HiP-AD repository):
@@ -20,6 +22,10 @@
  *   projects/mmdet3d_plugin/ops/src/deformable_aggregation.cpp:31-62, 86-124
  *       ATen glue (shape extraction, at::zeros) -> done by the Python host
  *       (hip-ad_b200/ops/deformable_aggregation.py) on top of this ABI.
+ *
+ * Alignment: mc_ms_feat, output, grad_output, grad_mc_ms_feat, weights and grad_weights should be 16-byte aligned
+ * (the 16-byte vector kernels are used then; otherwise a scalar kernel family is); sample_location,
+ * grad_sampling_location and sample_location_out MUST be 8-byte aligned (HIPAD_DFA_ERR_BAD_ARGUMENT otherwise).
  *
  * Tensor layouts (row-major, identical to the reference, deformable_aggregation.cpp:22-28):
  *   mc_ms_feat        [bs, num_feat, num_embeds]               f32 or bf16
@@ -143,6 +149,57 @@ int hipad_dfa_backward_stages(int feat_is_bf16, int stage_mask,
                               int batch_size, int num_cams, int num_feat, int num_embeds,
                               int num_scale, int num_anchors, int num_pts, int num_groups,
                               void *workspace, size_t workspace_bytes, void *stream);
+
+/* ---- grouped launches ("next" row f1 of the scope table) ----
+ * The aggregation calls of one decoder layer (det, map, plan, ego queries; sparse_onedecoder.py:867-887 of the
+ * reference issues them one after the other) read the SAME feature maps.  A group runs them as ONE forward launch and
+ * ONE backward chain, with ONE feature gradient for the whole group:
+ *   output / grad_output are PACKED [bs, A_total, C] (A_total = sum of the calls' num_anchors; call k owns rows
+ *   [sum_{j<k} A_j, +A_k) of every batch element), grad_mc_ms_feat is the sum of the calls' feature gradients.
+ * Returns HIPAD_DFA_ERR_UNSUPPORTED for layouts the grouped kernels do not cover (anything but 4 levels, <= 8
+ * groups, C = 128/256 f32 or C = 256 bf16): callers then issue the calls one by one. */
+#define HIPAD_DFA_MAX_GROUP_CALLS 8
+typedef struct hipad_dfa_call_t {
+    const float *sample_location;      /* [bs, A, P, cams, 2], 8-byte aligned */
+    const float *weights;              /* [bs, A, P, cams, L, G], 16-byte aligned */
+    float *grad_sampling_location;     /* backward only, 8-byte aligned */
+    float *grad_weights;               /* backward only, 16-byte aligned */
+    int32_t num_anchors;
+    int32_t num_pts;
+} hipad_dfa_call_t;
+
+size_t hipad_dfa_group_forward_workspace_bytes(const hipad_dfa_call_t *calls, int num_calls,
+                                               int batch_size, int num_cams, int num_embeds);
+
+/* workspace (256-byte aligned) holds the partial rows of output rows that are cut into several work units; it may be
+ * NULL when every call has num_pts*num_cams <= 128. */
+int hipad_dfa_group_forward(int feat_is_bf16, float *output_packed, const void *mc_ms_feat,
+                            const int32_t *spatial_shape, const int32_t *scale_start_index,
+                            const hipad_dfa_call_t *calls, int num_calls,
+                            int batch_size, int num_cams, int num_feat, int num_embeds,
+                            int num_scale, int num_groups,
+                            void *workspace, size_t workspace_bytes, void *stream);
+
+size_t hipad_dfa_group_backward_workspace_bytes(const hipad_dfa_call_t *calls, int num_calls,
+                                                int batch_size, int num_cams, int num_feat,
+                                                int num_embeds, int num_scale, int num_groups);
+
+/* grad_feat_flags: bit0 accumulate into grad_mc_ms_feat (no zero fill, touched rows read-modify-written);
+ *                  bit1 grad_mc_ms_feat is fp32 whatever the feature type (a shared accumulation buffer stays fp32
+ *                       and is narrowed once by its owner).
+ * grad_mc_ms_feat may be NULL (frozen features): only the calls' location / weight gradients are written. */
+int hipad_dfa_group_backward(int feat_is_bf16, int grad_feat_flags, const void *mc_ms_feat,
+                             const int32_t *spatial_shape, const int32_t *scale_start_index,
+                             const hipad_dfa_call_t *calls, int num_calls,
+                             const float *grad_output_packed, void *grad_mc_ms_feat,
+                             int batch_size, int num_cams, int num_feat, int num_embeds,
+                             int num_scale, int num_groups,
+                             void *workspace, size_t workspace_bytes, void *stream);
+
+/* Debugging: byte offset of the backward's 8 work counters inside its workspace (part items, -, partial slots used,
+ * tiny rows, reduce queue head, ...). */
+size_t hipad_dfa_debug_counters_offset(int batch_size, int num_cams, int num_feat, int num_embeds,
+                                       int num_scale, int num_anchors, int num_pts, int num_groups);
 
 /* ---- integer sampling contract (parity instrument) ----
  * indices: int32 [bs, A, P, cams, L, 6] = {valid, h_low, w_low, level_offset, corner_mask, row0},

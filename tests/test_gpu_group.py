@@ -1,0 +1,288 @@
+"""GPU tests of the grouped launches and of the parity-breadth cases VERDICT round 1 asked for:
+full-size map / plan / ego calls against the C oracle and against the reference's own CUDA op, fp32 and bf16.
+
+A group = the aggregation calls of one decoder layer (they read the same feature maps): one forward launch, one backward
+chain, one feature gradient.  Checked against the per-call oracle results (outputs, location / weight gradients per
+call, feature gradient = sum over calls), bitwise run-to-run, and through the public Python API.
+"""
+import numpy as np
+import pytest
+import torch
+
+import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+FP32_TOL = 1e-5
+BF16_TOL = 2e-2
+SMALL_LV = [(16, 28), (8, 14), (4, 7), (2, 4)]
+
+
+def rel_err(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+def dev(x, dtype=None):
+    t = torch.as_tensor(np.ascontiguousarray(x)).cuda()
+    return t if dtype is None else t.to(dtype)
+
+
+@pytest.fixture(scope="module")
+def ops(cuda_lib):
+    assert torch.cuda.is_available()
+    import hipad_b200
+    return hipad_b200.ops
+
+
+def _reference_ext():
+    from oracle import build_ref
+    if not build_ref.available():
+        pytest.skip("oracle/_ref not built")
+    return build_ref.load()
+
+
+def make_group(seed, bs, level_hw, final_hw, shapes_ap, C=256, G=8, geo=True):
+    """calls of one layer on ONE feature tensor: list of dicts (loc, weights, grad_out) + shared feat/shapes/starts."""
+    rng = np.random.default_rng(seed)
+    shapes, starts, F = H.level_tables(level_hw, 6)
+    feat = rng.standard_normal((bs, F, C), dtype=np.float32)
+    calls = []
+    for i, (kind, A, P) in enumerate(shapes_ap):
+        if geo:
+            c = H.make_geo_case(seed * 100 + i, "det" if kind == "ego" else kind, bs, level_hw, final_hw, C=C, G=G, A=A, P=P,
+                                with_feat=False)
+            loc, w = c["loc"], c["weights"]
+            if kind == "ego":          # visible to no camera
+                loc = np.full_like(loc, -0.5)
+        else:
+            c = H.make_case(seed * 100 + i, bs, 6, level_hw, C, G, A, P)
+            loc, w = c["loc"], c["weights"]
+        calls.append(dict(loc=loc, weights=w, grad_out=rng.standard_normal((bs, A, C), dtype=np.float32)))
+    return dict(feat=feat, shapes=shapes, starts=starts, calls=calls)
+
+
+def run_group(ops, g, bf16=False, shared=False, grouped=True):
+    feat = dev(g["feat"], torch.bfloat16 if bf16 else None).requires_grad_(True)
+    f = ops.share_feature_gradient(feat) if shared else feat
+    sh, st = dev(g["shapes"]).long(), dev(g["starts"]).long()
+    leaves = [(dev(c["loc"]).requires_grad_(True), dev(c["weights"]).requires_grad_(True)) for c in g["calls"]]
+    if grouped:
+        outs = ops.deformable_aggregation_group(f, sh, st, leaves)
+    else:
+        outs = [ops.deformable_aggregation_function(f, sh, st, l, w) for l, w in leaves]
+    torch.autograd.backward(outs, [dev(c["grad_out"]) for c in g["calls"]])
+    torch.cuda.synchronize()
+    return ([o.detach().cpu().numpy() for o in outs], feat.grad.float().cpu().numpy(),
+            [(l.grad.cpu().numpy(), w.grad.cpu().numpy()) for l, w in leaves])
+
+
+def oracle_group(oracle_mod, g, feat=None):
+    feat = g["feat"] if feat is None else feat
+    outs, leaves, g_feat = [], [], np.zeros(g["feat"].shape, np.float64)
+    for c in g["calls"]:
+        outs.append(oracle_mod.forward(feat, g["shapes"], g["starts"], c["loc"], c["weights"]))
+        gf, gl, gw = oracle_mod.backward(feat, g["shapes"], g["starts"], c["loc"], c["weights"], c["grad_out"])
+        g_feat += gf
+        leaves.append((gl, gw))
+    return outs, g_feat, leaves
+
+
+SMALL_GROUP = [("det", 40, 13), ("map", 10, 300), ("plan", 48, 90), ("ego", 1, 13)]
+
+
+@pytest.mark.parametrize("bs", [1, 2])
+@pytest.mark.parametrize("geo", [True, False])
+def test_group_matches_oracle_small(ops, oracle_mod, bs, geo):
+    g = make_group(3, bs, SMALL_LV, (64, 112), SMALL_GROUP, geo=geo)
+    outs, g_feat, leaves = run_group(ops, g)
+    r_outs, r_feat, r_leaves = oracle_group(oracle_mod, g)
+    for o, r in zip(outs, r_outs):
+        assert o.shape == r.shape and rel_err(o, r) <= FP32_TOL
+    assert rel_err(g_feat, r_feat) <= FP32_TOL
+    for (gl, gw), (rl, rw), c in zip(leaves, r_leaves, g["calls"]):
+        assert rel_err(gl, rl) <= FP32_TOL and rel_err(gw, rw) <= FP32_TOL
+        vis = ((c["loc"] > 0) & (c["loc"] < 1)).all(-1)
+        assert not gl[~vis].any() and not gw[~vis].any()
+    assert not g_feat[r_feat == 0].any()          # untouched rows are exact zeros
+
+
+def test_group_equals_per_call_results_and_is_reproducible(ops):
+    g = make_group(4, 2, SMALL_LV, (64, 112), SMALL_GROUP)
+    a = run_group(ops, g, grouped=True)
+    b = run_group(ops, g, grouped=True)
+    c = run_group(ops, g, grouped=False)
+    for x, y in zip(a[0], b[0]):
+        assert np.array_equal(x, y)
+    assert np.array_equal(a[1], b[1])
+    for (l0, w0), (l1, w1) in zip(a[2], b[2]):
+        assert np.array_equal(l0, l1) and np.array_equal(w0, w1)
+    # grouped vs one call at a time: the same kernels on the same work units -> identical outputs and per-call
+    # gradients; the feature gradient differs only in fp32 summation order (union of the calls vs autograd's sum)
+    for x, y in zip(a[0], c[0]):
+        assert np.array_equal(x, y)
+    for (l0, w0), (l1, w1) in zip(a[2], c[2]):
+        assert np.array_equal(l0, l1) and np.array_equal(w0, w1)
+    assert rel_err(a[1], c[1]) <= FP32_TOL
+
+
+@pytest.mark.parametrize("bf16", [False, True])
+def test_group_stage2_layer_full_size(ops, oracle_mod, bf16):
+    """One stage-2 decoder layer at 352x640: det 900x13 + map 100x300 + plan 480x90 + ego 1x13 in one group."""
+    g = make_group(5, 1, H.LEVELS_352x640, (352, 640), [("det", 900, 13), ("map", 100, 300), ("plan", 480, 90), ("ego", 1, 13)])
+    outs, g_feat, leaves = run_group(ops, g, bf16=bf16)
+    feat = torch.as_tensor(g["feat"]).bfloat16().float().numpy() if bf16 else g["feat"]
+    r_outs, r_feat, r_leaves = oracle_group(oracle_mod, g, feat)
+    for o, r in zip(outs, r_outs):
+        assert rel_err(o, r) <= FP32_TOL
+    assert rel_err(g_feat, r_feat) <= (BF16_TOL if bf16 else FP32_TOL)
+    for (gl, gw), (rl, rw) in zip(leaves, r_leaves):
+        assert rel_err(gl, rl) <= FP32_TOL and rel_err(gw, rw) <= FP32_TOL
+    assert not outs[3].any() and not leaves[3][0].any() and not leaves[3][1].any()      # ego: nothing visible
+
+
+@pytest.mark.parametrize("bf16", [False, True])
+def test_group_with_shared_step_buffer(ops, oracle_mod, bf16):
+    """Two groups (two decoder layers) accumulating into ONE fp32 step buffer via share_feature_gradient."""
+    g1 = make_group(6, 2, SMALL_LV, (64, 112), SMALL_GROUP)
+    g2 = make_group(7, 2, SMALL_LV, (64, 112), SMALL_GROUP)
+    g2["feat"] = g1["feat"]
+    feat = dev(g1["feat"], torch.bfloat16 if bf16 else None).requires_grad_(True)
+    f = ops.share_feature_gradient(feat)
+    sh, st = dev(g1["shapes"]).long(), dev(g1["starts"]).long()
+    outs, gos = [], []
+    for g in (g1, g2):
+        leaves = [(dev(c["loc"]).requires_grad_(True), dev(c["weights"]).requires_grad_(True)) for c in g["calls"]]
+        outs += ops.deformable_aggregation_group(f, sh, st, leaves)
+        gos += [dev(c["grad_out"]) for c in g["calls"]]
+    torch.autograd.backward(outs, gos)
+    torch.cuda.synchronize()
+    fr = torch.as_tensor(g1["feat"]).bfloat16().float().numpy() if bf16 else g1["feat"]
+    ref = oracle_group(oracle_mod, g1, fr)[1] + oracle_group(oracle_mod, g2, fr)[1]
+    # fp32 accumulation across all 8 calls, ONE rounding to bf16 at the end
+    assert rel_err(feat.grad.float().cpu().numpy(), ref) <= (4e-3 if bf16 else FP32_TOL)
+
+
+def test_shared_buffer_does_not_leak_between_backward_passes(ops, oracle_mod):
+    """a pass that never reaches the sink node must not leave a stale buffer behind."""
+    g = make_group(8, 1, SMALL_LV, (64, 112), SMALL_GROUP[:2])
+    feat = dev(g["feat"]).requires_grad_(True)
+    f = ops.share_feature_gradient(feat)
+    sh, st = dev(g["shapes"]).long(), dev(g["starts"]).long()
+    leaves = [(dev(c["loc"]).requires_grad_(True), dev(c["weights"]).requires_grad_(True)) for c in g["calls"]]
+    outs = [ops.deformable_aggregation_function(f, sh, st, l, w) for l, w in leaves]
+    gos = [dev(c["grad_out"]) for c in g["calls"]]
+    # pass 1: gradients w.r.t. the locations only -- the sink never runs
+    torch.autograd.grad(outs, [l for l, _ in leaves], gos, retain_graph=True)
+    # pass 2 and 3: full backward twice on the retained graph
+    torch.autograd.backward(outs, gos, retain_graph=True)
+    first = feat.grad.clone()
+    feat.grad = None
+    torch.autograd.backward(outs, gos)
+    torch.cuda.synchronize()
+    ref = oracle_group(oracle_mod, g)[1]
+    assert rel_err(first.cpu().numpy(), ref) <= FP32_TOL
+    assert torch.equal(first, feat.grad)
+
+
+def test_group_abi_rejects_bad_arguments(ops, cuda_lib):
+    from hipad_b200 import _lib
+    import ctypes
+    g = make_group(9, 1, SMALL_LV, (64, 112), SMALL_GROUP[:1])
+    feat, loc, w = dev(g["feat"]), dev(g["calls"][0]["loc"]), dev(g["calls"][0]["weights"])
+    sh, st = dev(g["shapes"]).int(), dev(g["starts"]).int()
+    out = torch.empty((1, 40, 256), device="cuda")
+    tab = _lib.call_table([(loc.data_ptr(), w.data_ptr(), None, None, 40, 13)])
+    tp = ctypes.cast(tab, ctypes.c_void_p)
+    s = torch.cuda.current_stream().cuda_stream
+    F = feat.shape[1]
+    assert cuda_lib.hipad_dfa_group_forward(0, out.data_ptr(), feat.data_ptr(), sh.data_ptr(), st.data_ptr(), tp, 0,
+                                            1, 6, F, 256, 4, 8, None, 0, s) == -1
+    assert cuda_lib.hipad_dfa_group_forward(0, None, feat.data_ptr(), sh.data_ptr(), st.data_ptr(), tp, 1,
+                                            1, 6, F, 256, 4, 8, None, 0, s) == -1
+    # 5 levels: outside the grouped kernels' family -> UNSUPPORTED (callers go call by call)
+    assert cuda_lib.hipad_dfa_group_forward(0, out.data_ptr(), feat.data_ptr(), sh.data_ptr(), st.data_ptr(), tp, 1,
+                                            1, 6, F, 256, 5, 8, None, 0, s) == -2
+    # backward without gradient buffers for the call
+    assert cuda_lib.hipad_dfa_group_backward(0, 0, feat.data_ptr(), sh.data_ptr(), st.data_ptr(), tp, 1, out.data_ptr(),
+                                             None, 1, 6, F, 256, 4, 8, None, 0, s) == -1
+
+
+# ------------------------------------------------------------------------------------- parity breadth (VERDICT weak #1)
+@pytest.mark.parametrize("kind,A,P", [("map", 100, 300), ("plan", 480, 90), ("ego", 1, 13)])
+@pytest.mark.parametrize("bf16", [False, True])
+def test_stage2_map_plan_ego_full_size_vs_oracle(ops, oracle_mod, kind, A, P, bf16):
+    g = make_group(10, 1, H.LEVELS_352x640, (352, 640), [(kind, A, P)])
+    outs, g_feat, leaves = run_group(ops, g, bf16=bf16, grouped=False)
+    feat = torch.as_tensor(g["feat"]).bfloat16().float().numpy() if bf16 else g["feat"]
+    r_outs, r_feat, r_leaves = oracle_group(oracle_mod, g, feat)
+    assert rel_err(outs[0], r_outs[0]) <= FP32_TOL
+    assert rel_err(g_feat, r_feat) <= (BF16_TOL if bf16 else FP32_TOL)
+    assert rel_err(leaves[0][0], r_leaves[0][0]) <= FP32_TOL and rel_err(leaves[0][1], r_leaves[0][1]) <= FP32_TOL
+
+
+@pytest.mark.parametrize("kind,A,P", [("map", 100, 300), ("plan", 480, 90), ("ego", 1, 13)])
+def test_stage2_map_plan_ego_full_size_vs_reference_cuda_op(ops, kind, A, P):
+    ext = _reference_ext()
+    g = make_group(11, 1, H.LEVELS_352x640, (352, 640), [(kind, A, P)])
+    c = g["calls"][0]
+    feat, loc, w, go = dev(g["feat"]), dev(c["loc"]), dev(c["weights"]), dev(c["grad_out"])
+    shapes, starts = dev(g["shapes"]), dev(g["starts"])
+    ref_out = ext.deformable_aggregation_forward(feat, shapes, starts, loc, w)
+    r_feat, r_loc, r_w = torch.zeros_like(feat), torch.zeros_like(loc), torch.zeros_like(w)
+    ext.deformable_aggregation_backward(feat, shapes, starts, loc, w, go, r_feat, r_loc, r_w)
+    outs, g_feat, leaves = run_group(ops, g, grouped=False)
+    assert rel_err(outs[0], ref_out.cpu().numpy()) <= FP32_TOL
+    assert rel_err(g_feat, r_feat.cpu().numpy()) <= FP32_TOL
+    assert rel_err(leaves[0][0], r_loc.cpu().numpy()) <= FP32_TOL
+    assert rel_err(leaves[0][1], r_w.cpu().numpy()) <= FP32_TOL
+
+
+def test_hires_512x1408_layer_bs2(ops, oracle_mod):
+    """BASELINE configs[4] geometry (the only HBM-resident case), stage-1 plan size, two samples, grouped."""
+    g = make_group(12, 2, H.LEVELS_512x1408, (512, 1408), [("det", 900, 13), ("map", 100, 300), ("plan", 48, 90), ("ego", 1, 13)])
+    outs, g_feat, leaves = run_group(ops, g)
+    r_outs, r_feat, r_leaves = oracle_group(oracle_mod, g)
+    for o, r in zip(outs, r_outs):
+        assert rel_err(o, r) <= FP32_TOL
+    assert rel_err(g_feat, r_feat) <= FP32_TOL
+    for (gl, gw), (rl, rw) in zip(leaves, r_leaves):
+        assert rel_err(gl, rl) <= FP32_TOL and rel_err(gw, rw) <= FP32_TOL
+
+
+def test_reference_op_cells_at_near_integer_coordinates(ops):
+    """the integer contract against the COMPILED reference op, not only our oracle.  The forward value
+    is continuous across a cell boundary, the location gradient is not (it is the slope inside the cell the sample was
+    floored into), so agreeing location gradients at coordinates within a few ulps of pixel centres / edges show that
+    both implementations floor the same way (one fused multiply-add, SURVEY.md §7 "Bit-exact indices")."""
+    ext = _reference_ext()
+    lv = [(16, 28), (7, 13)]
+    shapes, starts, F = H.level_tables(lv, 2)
+    C, G, A, P = 32, 1, 2048, 2
+    rng = np.random.default_rng(0)
+    n = A * P * 2
+    W = np.where(rng.random(n) < 0.5, 28, 13).astype(np.float32)
+    Hh = np.where(W == 28, 16, 7).astype(np.float32)
+    x = ((rng.integers(0, 28, n) % W + 0.5) / W).astype(np.float32)      # exactly a pixel centre at one level
+    y = ((rng.integers(0, 16, n) % Hh + 0.5) / Hh).astype(np.float32)
+    for _ in range(3):                                                    # and up to 3 ulps to either side
+        step = rng.integers(-1, 2, n)
+        x = np.where(step > 0, np.nextafter(x, np.float32(2)), np.where(step < 0, np.nextafter(x, np.float32(-2)), x))
+        step = rng.integers(-1, 2, n)
+        y = np.where(step > 0, np.nextafter(y, np.float32(2)), np.where(step < 0, np.nextafter(y, np.float32(-2)), y))
+    loc = np.stack([x, y], -1).reshape(1, A, P, 2, 2).astype(np.float32)
+    feat = rng.standard_normal((1, F, C), dtype=np.float32)
+    w = rng.standard_normal((1, A, P, 2, 2, G), dtype=np.float32)
+    go = rng.standard_normal((1, A, C), dtype=np.float32)
+    f, l, ww, g = dev(feat), dev(loc), dev(w), dev(go)
+    sh, st = dev(shapes), dev(starts)
+    ref_out = ext.deformable_aggregation_forward(f, sh, st, l, ww)
+    r_feat, r_loc, r_w = torch.zeros_like(f), torch.zeros_like(l), torch.zeros_like(ww)
+    ext.deformable_aggregation_backward(f, sh, st, l, ww, g, r_feat, r_loc, r_w)
+    fl = l.clone().requires_grad_(True)
+    out = ops.deformable_aggregation_function(f, sh.long(), st.long(), fl, ww)
+    out.backward(g)
+    torch.cuda.synchronize()
+    assert rel_err(out.detach().cpu().numpy(), ref_out.cpu().numpy()) <= FP32_TOL
+    assert rel_err(fl.grad.cpu().numpy(), r_loc.cpu().numpy()) <= FP32_TOL
