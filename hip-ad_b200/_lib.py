@@ -32,6 +32,7 @@ _SIGNATURES = {
     "hipad_dfa_group_forward": ([_i, _p, _p, _p, _p, _p, _i] + [_i] * 6 + [_p, ctypes.c_size_t, _p], _i),
     "hipad_dfa_group_backward_workspace_bytes": ([_p, _i] + [_i] * 6, ctypes.c_size_t),
     "hipad_dfa_group_backward": ([_i, _i, _p, _p, _p, _p, _i, _p, _p] + [_i] * 6 + [_p, ctypes.c_size_t, _p], _i),
+    "hipad_dfa_group_backward_stages": ([_i, _i, _i, _p, _p, _p, _p, _i, _p, _p] + [_i] * 6 + [_p, ctypes.c_size_t, _p], _i),
     "hipad_dfa_debug_counters_offset": (_DIMS8, ctypes.c_size_t),
 }
 

@@ -236,6 +236,28 @@ int hipad_dfa_group_backward(int feat_is_bf16, int grad_feat_flags, const void* 
     return launch_group_backward(a);
 }
 
+int hipad_dfa_group_backward_stages(int feat_is_bf16, int grad_feat_flags, int stage_mask, const void* mc_ms_feat,
+                                    const int32_t* spatial_shape, const int32_t* scale_start_index,
+                                    const hipad_dfa_call_t* calls, int num_calls, const float* grad_output_packed,
+                                    void* grad_mc_ms_feat, int batch_size, int num_cams, int num_feat, int num_embeds,
+                                    int num_scale, int num_groups, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!mc_ms_feat || !spatial_shape || !scale_start_index || !grad_output_packed || !grad_mc_ms_feat ||
+        bad_dims(batch_size, num_cams, num_feat, num_embeds, num_scale, 1, 1, num_groups))
+        return HIPAD_DFA_ERR_BAD_ARGUMENT;
+    GroupBwdArgs a = {};
+    if (int rc = fill_calls(a.calls, calls, num_calls, true)) return rc;
+    a.type = feat_is_bf16 ? kBF16 : kF32; a.feat = mc_ms_feat; a.shapes = spatial_shape; a.starts = scale_start_index;
+    a.ncalls = num_calls; a.grad_out = grad_output_packed; a.g_feat = grad_mc_ms_feat;
+    a.accumulate = (grad_feat_flags & 1) != 0;
+    a.g_feat_f32 = !feat_is_bf16 || (grad_feat_flags & 2) != 0;
+    a.bs = batch_size; a.cams = num_cams; a.num_feat = num_feat; a.C = num_embeds; a.L = num_scale; a.G = num_groups;
+    a.workspace = workspace; a.workspace_bytes = workspace_bytes;
+    a.stream = reinterpret_cast<cudaStream_t>(stream);
+    a.stage_mask = stage_mask & 7;
+    a.separate_zero_fill = (stage_mask & 8) != 0;
+    return launch_group_backward(a);
+}
+
 int hipad_dfa_sample_indices(int32_t* indices, const int32_t* spatial_shape, const int32_t* scale_start_index,
                              const float* sample_location, int batch_size, int num_cams, int num_scale,
                              int num_anchors, int num_pts, void* stream) {

@@ -53,7 +53,7 @@ int launch_forward(const FwdArgs& a) {
     if (!ks.ok || d.cams * d.L > kMaxCamLevels || (long long)d.num_feat * d.C >= (1LL << 30)) return -2;
     const int mode = a.fused ? kFused : kFwd;
     if (a.fused && (256 % d.G != 0)) return -2;
-    if (!a.fused && al && d.P * d.cams <= 128 && group_kernel_supported(a.type, d.C, d.L, d.G, d.cams)) {
+    if (!a.fused && al && d.P * d.cams <= 96 && group_kernel_supported(a.type, d.C, d.L, d.G, d.cams)) {
         // whole rows fit one work unit: the grouped kernel (dfa_group.cuh) with a single call and no workspace
         GroupFwdArgs g = {};
         g.type = a.type; g.out = a.out; g.feat = a.feat; g.shapes = a.shapes; g.starts = a.starts;

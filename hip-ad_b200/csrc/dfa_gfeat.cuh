@@ -345,12 +345,12 @@ __device__ void band_sort_body(const GfeatParams& p, const BandCtx& bc, W* a, W*
     float* recw = p.recw + (((size_t)bc.b_idx * d.cams * d.L + bc.cl) * AP + bc.base) * d.G;
     const int lvl = bc.cl - bc.cam * d.L;
     const W vmask = ((W)1 << bc.vb) - 1;
-    for (int i0 = 0; i0 < bc.n; i0 += kSortThreads * 4) {
-        int sid[4], arow[4];
-        float2 xy[4];
-        const float* wsrc[4];
+    for (int i0 = 0; i0 < bc.n; i0 += kSortThreads * 2) {
+        int sid[2], arow[2];
+        float2 xy[2];
+        const float* wsrc[2];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < 2; ++u) {
             const int i = i0 + u * kSortThreads + tid;
             sid[u] = (i < bc.n) ? (int)(sorted[i] & vmask) : p.calls[0].id_begin;
             const GfeatCall& gc = p.calls[call_of_id(p, sid[u])];
@@ -361,7 +361,7 @@ __device__ void band_sort_body(const GfeatParams& p, const BandCtx& bc, W* a, W*
             arow[u] = gc.anchor_begin + s_local / gc.P;
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < 2; ++u) {
             const int i = i0 + u * kSortThreads + tid;
             if (i < bc.n) {
                 const Quad q = quad_setup(xy[u].x, xy[u].y, bc.h, bc.w);
@@ -397,7 +397,7 @@ inline size_t band_sort_smem_bytes(int n_chunks) {
 }
 
 // grid (NB, cams*L, bs), block kSortThreads
-__global__ void __launch_bounds__(kSortThreads) dfa_band_sort_kernel(const GfeatParams p) {
+__global__ void __launch_bounds__(kSortThreads, 2) dfa_band_sort_kernel(const GfeatParams p) {
     const Dims d = p.d;
     const int band = blockIdx.x, cl = blockIdx.y, b_idx = blockIdx.z;
     const int cam = cl / d.L;

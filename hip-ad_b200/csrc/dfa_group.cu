@@ -10,34 +10,37 @@ namespace {
 constexpr size_t kAlignG = 256;
 inline size_t align_g(size_t v) { return (v + kAlignG - 1) / kAlignG * kAlignG; }
 
-inline int group_warps() {
-    const int w = hipad_env_int("HIPAD_DFA_GROUP_WARPS", 4);
-    return (w == 8) ? 8 : 4;
-}
-// (p,cam) pairs per unit: the forward keeps whole det rows (78 pairs) in one unit; the backward's metadata is
-// larger per pair (shared memory per CTA decides how many CTAs an SM holds), so its units are half as long
+inline int group_warps() { return 4; }     // measured: 8-warp CTAs are 1.3x slower (r2b)
+// (p,cam) pairs per unit.  Longer units find more key points of an anchor in the same quad (fewer gathers) but hold
+// more shared memory, which is taken from the L1 cache the gather lives on
 inline int group_ps_max(bool bwd) {
-    const int dflt = bwd ? 64 : 128;
+    const int dflt = kGroupMaxPS;
     const int v = hipad_env_int(bwd ? "HIPAD_DFA_GROUP_PS_BWD" : "HIPAD_DFA_GROUP_PS_FWD", dflt);
     return (v >= 16 && v <= kGroupMaxPS) ? v : dflt;
 }
 
-template <typename T, int V, int NCH, bool kBwd, int kW>
+template <typename T, int V, int NCH, bool kBwd, int kW, int kDepth, int kMinCtas>
 int launch_inst(const GroupParams& gp, int grid, size_t smem, cudaStream_t st) {
-    auto kern = dfa_group_kernel<T, V, NCH, kBwd, kW>;
+    auto kern = dfa_group_kernel<T, V, NCH, kBwd, kW, kDepth, kMinCtas>;
     cudaError_t e = ensure_smem(kern, smem);
     if (e != cudaSuccess) return (int)e;
     kern<<<grid, kW * 32, smem, st>>>(gp);
     return (int)cudaGetLastError();
 }
 
-template <bool kBwd, int kW>
-int dispatch(ElemType t, const GroupParams& gp, int grid, size_t smem, cudaStream_t st) {
+// deep = 2 quads in flight per warp for fp32 rows (4 for packed bf16), 128 registers, 4 CTAs of 4 warps per SM;
+// shallow (default) = 1 (2) in flight, <= 80 registers, 6 CTAs per SM: more units resident, so the per-unit
+// visibility / sort phases of some overlap the gather of others (measured, stage-2 layer: forward 92 vs 119 us,
+// backward 311 vs 336 us; HIPAD_DFA_GROUP_DEEP=1 selects the deep variant)
+template <bool kBwd>
+int dispatch(ElemType t, bool deep, const GroupParams& gp, int grid, size_t smem, cudaStream_t st) {
     if (t == kF32) {
-        if (gp.C == 128) return launch_inst<float, 4, 1, kBwd, kW>(gp, grid, smem, st);
-        if (gp.C == 256) return launch_inst<float, 4, 2, kBwd, kW>(gp, grid, smem, st);
+        if (gp.C == 128) return launch_inst<float, 4, 1, kBwd, 4, 2, 5>(gp, grid, smem, st);
+        if (gp.C == 256) return deep ? launch_inst<float, 4, 2, kBwd, 4, 2, 4>(gp, grid, smem, st)
+                                     : launch_inst<float, 4, 2, kBwd, 4, 1, 6>(gp, grid, smem, st);
     } else {
-        if (gp.C == 256) return launch_inst<__nv_bfloat16, 8, 1, kBwd, kW>(gp, grid, smem, st);
+        if (gp.C == 256) return deep ? launch_inst<__nv_bfloat16, 8, 1, kBwd, 4, 4, 4>(gp, grid, smem, st)
+                                     : launch_inst<__nv_bfloat16, 8, 1, kBwd, 4, 2, 5>(gp, grid, smem, st);
     }
     return -2;
 }
@@ -50,7 +53,7 @@ bool group_kernel_supported(ElemType t, int C, int L, int G, int cams) {
     const int gd = C / G;
     if (gd % V != 0) return false;
     const int lpg = gd / V;
-    if (lpg > 32 || (lpg & (lpg - 1)) != 0) return false;
+    if (lpg < 4 || lpg > 32 || (lpg & (lpg - 1)) != 0) return false;   // the backward's transposing butterfly needs >= 4 lanes
     if (t == kF32) return C == 128 || C == 256;
     return C == 256;
 }
@@ -64,7 +67,11 @@ GroupPlan plan_group(bool bwd, const CallDesc* calls, int ncalls, int bs, int ca
         const int NP = calls[k].P * cams;
         int S = forced_single_slice ? 1 : (NP + ps_cap - 1) / ps_cap;
         if (S < 1) S = 1;
-        const int PS = (NP + S - 1) / S;
+        int PS = (NP + S - 1) / S;
+        if (!forced_single_slice) {                   // whole key points per slice (all cameras of a point together)
+            const int up = (PS + cams - 1) / cams * cams;
+            if (up <= ps_cap || up <= cams) PS = up;
+        }
         S = (NP + PS - 1) / PS;                       // no empty slice
         pl.S[k] = S;
         pl.PS[k] = PS;
@@ -125,8 +132,8 @@ int launch_group_sample(bool bwd, ElemType t, const GroupParams& gp, long long u
     g.so = group_smem_layout(bwd, gp.ps_max, nch * 32 * V, kw);
     const size_t smem = (size_t)g.so.total;
     if (smem > kSampleSmemBudget) return -2;
-    if (bwd) return kw == 8 ? dispatch<true, 8>(t, g, (int)units, smem, st) : dispatch<true, 4>(t, g, (int)units, smem, st);
-    return kw == 8 ? dispatch<false, 8>(t, g, (int)units, smem, st) : dispatch<false, 4>(t, g, (int)units, smem, st);
+    const bool deep = hipad_env_int("HIPAD_DFA_GROUP_DEEP", 0) != 0;
+    return bwd ? dispatch<true>(t, deep, g, (int)units, smem, st) : dispatch<false>(t, deep, g, (int)units, smem, st);
 }
 
 int launch_group_forward(const GroupFwdArgs& a) {

@@ -1,15 +1,24 @@
 // dfa_group.cuh — grouped sample-major kernel: ONE launch for several aggregation calls that read the same
 // feature maps (the det / map / plan / ego calls of a decoder layer, sparse_onedecoder.py:867-887), also used
 // with a single call.  Specialised for the shipped HiP-AD layout: 16-byte vector rows (C = NCH*32*V), 4 levels,
-// <= 8 groups; everything else stays on dfa_sample.cuh.
+// <= 8 groups, >= 4 lanes per channel group; everything else stays on dfa_sample.cuh.
 //
-// Compared with dfa_sample_kernel (round 1):
-//   * work unit = (call, output row, CONTIGUOUS range of <= 128 (p,cam) pairs), one CTA of kW warps each; a launch
-//     has thousands of similar units (no cluster, no per-call tail), the slices of a row are combined through
-//     partial rows + a ticket (the last CTA to arrive adds the partials in slice order: deterministic);
-//   * the weights of an item (8 floats) are staged in shared memory by the metadata pass, so the gather loop issues
-//     nothing but the 4 corner rows; forward items are dealt to warps one by one (balanced), not pair by pair;
-//   * address arithmetic per corner is one 64-bit add of a 32-bit byte offset to a lane-resolved base.
+// Work unit = (call, output row, CONTIGUOUS range of <= 96 (p,cam) pairs), one CTA of kW warps; a launch has
+// thousands of similar units (no cluster, no per-call tail).  Inside a unit:
+//   1. visibility test + ordered compaction of the unit's pairs (10-20 % are visible);
+//   2. every (visible pair, level) ITEM gets a key (camera-level, quad row, quad column); a rank sort in shared
+//      memory brings items that read the SAME quad of the same map together — the key points of one anchor fall
+//      into a handful of quads on the coarse levels, so a unit has 1.5-3x fewer distinct quads than items;
+//   3. forward: per quad the bilinear coefficients x group weights of its items are summed into one
+//      [group][corner] table (weights read once, coalesced); the gather loop then reads each distinct quad ONCE
+//      (4 corner rows, LDG.128, two quads in flight per warp) and applies the merged table;
+//      backward: the gather loop reduces <grad_out, corner_k> per (quad, group) once (transposing butterfly, 4
+//      shuffles per 128 channels), and a thread-per-item epilogue turns those 32 numbers into the item's weight
+//      gradients and location-gradient terms;
+//   4. slices of a row are combined through partial rows + a ticket: the last CTA to arrive adds the partials in
+//      slice order (deterministic, no floating-point atomics anywhere).
+// Every floating-point sum has a fixed order: items of a quad in (pair, level) order, quads of a warp in list order,
+// warps in index order, slices in slice order.
 #pragma once
 #include "dfa_common.cuh"
 
@@ -17,8 +26,9 @@ namespace hipad {
 
 constexpr int kMaxGroupCalls = 8;
 constexpr int kGroupL = 4;          // levels (compile time)
-constexpr int kGroupMaxG = 8;       // weights of one item held as 8 floats in shared memory
-constexpr int kGroupMaxPS = 128;    // (p,cam) pairs per unit (one visibility pass of a 4-warp CTA)
+constexpr int kGroupMaxG = 8;       // groups held per quad table
+constexpr int kGroupMaxPS = 96;     // (p,cam) pairs per unit
+constexpr int kQuadChunk = 64;      // distinct quads whose tables are resident at a time
 
 struct GroupCall {
     const float* loc;        // [bs, A, P, cams, 2]
@@ -36,25 +46,31 @@ struct GroupCall {
 };
 
 struct GroupSmem {
-    int tab, wcnt, flag, vis, lxy, lpair, mrows, mcoef, mw, mdx, mdy, red, total;
+    int tab, wcnt, flag, vis, lxy, lpair, key, mask, lhlw, sorted, qof, qstart, gxy, qrows, qtab, total;
 };
 __host__ __device__ inline GroupSmem group_smem_layout(bool bwd, int ps_max, int cpad, int warps) {
     GroupSmem o;
     int b = 0;
     auto take = [&](int bytes) { const int at = b; b += (bytes + 15) & ~15; return at; };
-    const int items = ps_max * kGroupL;
+    const int items = ((ps_max + 3) & ~3) * kGroupL;       // level-major, every level padded to 4 entries
     o.tab = take(kMaxCamLevels * 3 * 4);
     o.wcnt = take(16 * 4);
     o.flag = take(16);
     o.vis = take(bwd ? ps_max : 0);
     o.lxy = take(ps_max * 8);
-    o.lpair = take(ps_max * 4);
-    o.mrows = take(items * 16);
-    o.mcoef = take(items * 16);
-    o.mw = take(items * kGroupMaxG * 4);
-    o.mdx = take(bwd ? items * 16 : 0);
-    o.mdy = take(bwd ? items * 16 : 0);
-    o.red = take(bwd ? 0 : warps * cpad * 4);
+    o.lpair = take(ps_max * 2);
+    o.key = take(items * 4);
+    o.mask = take(items);
+    o.lhlw = take(items * 8);
+    o.sorted = take(items * 2);
+    o.qof = take(items * 2);
+    o.qstart = take((items + 1) * 2);
+    o.gxy = take(bwd ? items * 8 : 0);
+    o.qrows = take(kQuadChunk * 16);
+    // quad tables [quad][group] float4; the forward's cross-warp reduction scratch reuses the same bytes
+    int qtab = kQuadChunk * kGroupMaxG * 16;
+    if (!bwd && warps * cpad * 4 > qtab) qtab = warps * cpad * 4;
+    o.qtab = take(qtab);
     o.total = b;
     return o;
 }
@@ -72,8 +88,14 @@ struct GroupParams {
     GroupCall calls[kMaxGroupCalls];
 };
 
-template <typename T, int V, int NCH, bool kBwd, int kW>
-__global__ void __launch_bounds__(kW * 32) dfa_group_kernel(const GroupParams p) {
+struct ItemGeo {
+    float lh, lw, hh, hw;
+};
+
+// kDepth: distinct quads whose rows are in flight per warp (registers: kDepth * 32 for fp32 C = 256);
+// kMinCtas: CTAs per SM the register allocation must allow
+template <typename T, int V, int NCH, bool kBwd, int kW, int kDepth, int kMinCtas>
+__global__ void __launch_bounds__(kW * 32, kMinCtas) dfa_group_kernel(const GroupParams p) {
     constexpr int kThreads = kW * 32;
     constexpr int L = kGroupL;
     constexpr int CPAD = NCH * 32 * V;                       // == C (checked on the host)
@@ -87,9 +109,10 @@ __global__ void __launch_bounds__(kW * 32) dfa_group_kernel(const GroupParams p)
         if (k < p.ncalls && (int)blockIdx.x >= p.calls[k].unit_begin) c = k;
     const GroupCall& gc = p.calls[c];
     const int A = gc.A, S = gc.S, PS = gc.PS;
-    const int NP = gc.P * p.cams;
-    const int r = (int)blockIdx.x - gc.unit_begin;
-    const int ba = r / S, slice = r - ba * S;
+    const int cams = p.cams;
+    const int NP = gc.P * cams;
+    const int r_unit = (int)blockIdx.x - gc.unit_begin;
+    const int ba = r_unit / S, slice = r_unit - ba * S;
     const int b = ba / A, a = ba - b * A;
     const int p0 = slice * PS;
     const int n_mine = min(PS, NP - p0);
@@ -102,13 +125,17 @@ __global__ void __launch_bounds__(kW * 32) dfa_group_kernel(const GroupParams p)
     int* s_flag = reinterpret_cast<int*>(smem_raw + so.flag);
     unsigned char* s_vis = smem_raw + so.vis;
     float2* l_xy = reinterpret_cast<float2*>(smem_raw + so.lxy);
-    int* l_pair = reinterpret_cast<int*>(smem_raw + so.lpair);
-    uint4* m_rows = reinterpret_cast<uint4*>(smem_raw + so.mrows);
-    float4* m_coef = reinterpret_cast<float4*>(smem_raw + so.mcoef);
-    float* m_w = reinterpret_cast<float*>(smem_raw + so.mw);
-    float4* m_dx = reinterpret_cast<float4*>(smem_raw + so.mdx);
-    float4* m_dy = reinterpret_cast<float4*>(smem_raw + so.mdy);
-    float* red = reinterpret_cast<float*>(smem_raw + so.red);
+    unsigned short* l_pair = reinterpret_cast<unsigned short*>(smem_raw + so.lpair);
+    unsigned* s_key = reinterpret_cast<unsigned*>(smem_raw + so.key);
+    unsigned char* s_mask = smem_raw + so.mask;
+    float2* s_lhlw = reinterpret_cast<float2*>(smem_raw + so.lhlw);
+    unsigned short* s_sorted = reinterpret_cast<unsigned short*>(smem_raw + so.sorted);
+    unsigned short* s_qof = reinterpret_cast<unsigned short*>(smem_raw + so.qof);
+    unsigned short* s_qstart = reinterpret_cast<unsigned short*>(smem_raw + so.qstart);
+    float2* s_gxy = reinterpret_cast<float2*>(smem_raw + so.gxy);
+    uint4* q_rows = reinterpret_cast<uint4*>(smem_raw + so.qrows);
+    float4* q_tab = reinterpret_cast<float4*>(smem_raw + so.qtab);
+    float* red = reinterpret_cast<float*>(smem_raw + so.qtab);
 
     if (kBwd && p.zero_n16 > 0) {
         // dense zero fill of the feature gradient, 1/gridDim of it per CTA: fire-and-forget stores that drain
@@ -119,12 +146,12 @@ __global__ void __launch_bounds__(kW * 32) dfa_group_kernel(const GroupParams p)
         const uint4 z = make_uint4(0u, 0u, 0u, 0u);
         for (long long i = z0 + tid; i < z1; i += kThreads) p.zero_ptr[i] = z;
     }
-    load_level_table(tab, p.shapes, p.starts, p.cams * L);
+    load_level_table(tab, p.shapes, p.starts, cams * L);
 
     // ------------------------------------------------------------------ phase 1: visible pairs (ordered compaction)
     const float2* loc2 = reinterpret_cast<const float2*>(gc.loc) + (size_t)ba * NP + p0;
     int n_list = 0;
-    for (int base = 0; base < n_mine; base += kThreads) {       // one trip for PS <= kThreads
+    for (int base = 0; base < n_mine; base += kThreads) {       // one trip (PS <= 96 <= kThreads)
         const int k = base + tid;
         float2 xy = make_float2(-1.f, -1.f);
         if (k < n_mine) xy = __ldg(loc2 + k);
@@ -147,7 +174,7 @@ __global__ void __launch_bounds__(kW * 32) dfa_group_kernel(const GroupParams p)
         if (vis) {
             const int slot = n_list + before + __popc(bal & ((1u << lane) - 1u));
             l_xy[slot] = xy;
-            l_pair[slot] = k;
+            l_pair[slot] = (unsigned short)k;
         }
         n_list += all;
         __syncthreads();
@@ -167,60 +194,101 @@ __global__ void __launch_bounds__(kW * 32) dfa_group_kernel(const GroupParams p)
         }
     }
 
-    // ------------------------------------------------------------------ phase 2: gather metadata, one thread per item
+    // ------------------------------------------------------------------ phase 2: item keys
+    // An ITEM is (visible pair i, level l), stored LEVEL-MAJOR at position l*n_pad + i (n_pad = n_list rounded up to 4,
+    // the padding holds keys that sort last): items of different levels never share a quad, so the sort below only
+    // looks at one level's segment.  key = camera (6 bits) | quad row + 1 (13) | quad column + 1 (13): level maps up to
+    // 8190 x 8190, at most 64 cameras.
+    const int n_pad = (n_list + 3) & ~3;
     const int n_items = n_list * L;
-    const unsigned row_bytes = (unsigned)p.C * (unsigned)sizeof(T);
-    for (int it = tid; it < n_items; it += kThreads) {
-        const int i = it >> 2, l = it & 3;
-        const float2 xy = l_xy[i];
-        const int pair = p0 + l_pair[i];
-        const int pt = pair / p.cams, cam = pair - pt * p.cams;
-        const int* t = tab + (cam * L + l) * 3;
-        const int h = t[0], w = t[1];
-        const Quad q = quad_setup(xy.x, xy.y, h, w);
-        const int r1 = t[2] + q.h_low * w + q.w_low, r2 = r1 + 1, r3 = r1 + w, r4 = r3 + 1;
-        // out-of-bounds corners are redirected to an in-bounds corner of the same quad with coefficient 0
-        const int safe = q.ok1 ? r1 : (q.ok2 ? r2 : (q.ok3 ? r3 : r4));
-        m_rows[it] = make_uint4((unsigned)(q.ok1 ? r1 : safe) * row_bytes, (unsigned)(q.ok2 ? r2 : safe) * row_bytes,
-                                (unsigned)(q.ok3 ? r3 : safe) * row_bytes, (unsigned)(q.ok4 ? r4 : safe) * row_bytes);
-        m_coef[it] = make_float4(q.ok1 ? q.hh * q.hw : 0.f, q.ok2 ? q.hh * q.lw : 0.f,
-                                 q.ok3 ? q.lh * q.hw : 0.f, q.ok4 ? q.lh * q.lw : 0.f);
-        const float* wsrc = gc.weights + (((size_t)ba * NP + pair) * L + l) * G;
-        float* wdst = m_w + it * kGroupMaxG;
-        if (G == 8) {
-            const float4 w0 = __ldg(reinterpret_cast<const float4*>(wsrc));
-            const float4 w1 = __ldg(reinterpret_cast<const float4*>(wsrc) + 1);
-            reinterpret_cast<float4*>(wdst)[0] = w0;
-            reinterpret_cast<float4*>(wdst)[1] = w1;
-        } else {
-            for (int g = 0; g < G; ++g) wdst[g] = __ldg(wsrc + g);
+    for (int idx = tid; idx < n_pad * L; idx += kThreads) {
+        const int i = idx >> 2, l = idx & 3;
+        unsigned key = 0xffffffffu;
+        if (i < n_list) {
+            const float2 xy = l_xy[i];
+            const int pair = p0 + l_pair[i];
+            const int cam = pair % cams;
+            const int* t = tab + (cam * L + l) * 3;
+            const Quad q = quad_setup(xy.x, xy.y, t[0], t[1]);
+            key = ((unsigned)cam << 26) | ((unsigned)(q.h_low + 1) << 13) | (unsigned)(q.w_low + 1);
+            s_mask[l * n_pad + i] = (unsigned char)((int)q.ok1 | ((int)q.ok2 << 1) | ((int)q.ok3 << 2) | ((int)q.ok4 << 3));
+            s_lhlw[l * n_pad + i] = make_float2(q.lh, q.lw);
         }
-        if (kBwd) {
-            // d(val)/d(loc_x) = W * (-hh v1 + hh v2 - lh v3 + lh v4), d/d(loc_y) = H * (-hw v1 - lw v2 + hw v3 + lw v4)
-            const float W_ = (float)w, H_ = (float)h;
-            m_dx[it] = make_float4(q.ok1 ? -q.hh * W_ : 0.f, q.ok2 ? q.hh * W_ : 0.f,
-                                   q.ok3 ? -q.lh * W_ : 0.f, q.ok4 ? q.lh * W_ : 0.f);
-            m_dy[it] = make_float4(q.ok1 ? -q.hw * H_ : 0.f, q.ok2 ? -q.lw * H_ : 0.f,
-                                   q.ok3 ? q.hw * H_ : 0.f, q.ok4 ? q.lw * H_ : 0.f);
-        }
+        s_key[l * n_pad + i] = key;
     }
     __syncthreads();
 
-    // ------------------------------------------------------------------ phase 3: gather
+    // ------------------------------------------------------------------ phase 3: rank sort inside each level
+    // (stable: ties by position).  Rank r of level l goes to slot l*n_list + r of the sorted list.
+    for (int idx = tid; idx < n_items; idx += kThreads) {
+        const int i = idx >> 2, l = idx & 3;
+        const unsigned* seg = s_key + l * n_pad;
+        const unsigned k = seg[i];
+        int rank = 0;
+        for (int j0 = 0; j0 < n_pad; j0 += 4) {
+            const uint4 kk = *reinterpret_cast<const uint4*>(seg + j0);
+            rank += (kk.x < k || (kk.x == k && j0 + 0 < i)) ? 1 : 0;
+            rank += (kk.y < k || (kk.y == k && j0 + 1 < i)) ? 1 : 0;
+            rank += (kk.z < k || (kk.z == k && j0 + 2 < i)) ? 1 : 0;
+            rank += (kk.w < k || (kk.w == k && j0 + 3 < i)) ? 1 : 0;
+        }
+        s_sorted[l * n_list + rank] = (unsigned short)(l * n_pad + i);
+    }
+    __syncthreads();
+
+    // ------------------------------------------------------------------ phase 4: distinct quads
+    // a quad starts wherever the sorted key changes; quad index of an item = number of starts up to its rank - 1
+    int n_quads = 0;
+    for (int base = 0; base < n_items; base += kThreads) {
+        const int r = base + tid;
+        bool head = false;
+        int it = 0;
+        if (r < n_items) {
+            it = s_sorted[r];
+            // a quad starts where the key changes or a new level's segment begins (n_list ranks per level)
+            const int lv = (r >= n_list) + (r >= 2 * n_list) + (r >= 3 * n_list);
+            head = (r == lv * n_list) || (s_key[it] != s_key[s_sorted[r - 1]]);
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, head);
+        if (lane == 0) s_wcnt[warp] = __popc(bal);
+        __syncthreads();
+        int before = 0, all = 0;
+#pragma unroll
+        for (int w = 0; w < kW; ++w) {
+            const int cnt = s_wcnt[w];
+            if (w < warp) before += cnt;
+            all += cnt;
+        }
+        if (r < n_items) {
+            const int q = n_quads + before + __popc(bal & ((2u << lane) - 1u)) - 1;     // inclusive count - 1
+            s_qof[it] = (unsigned short)q;
+            if (head) s_qstart[q] = (unsigned short)r;
+        }
+        n_quads += all;
+        __syncthreads();
+    }
+    if (tid == 0) s_qstart[n_quads] = (unsigned short)n_items;
+    __syncthreads();
+
+    // position of an item in the level-major arrays -> its level
+    auto level_of = [&](int pos) { return (pos >= n_pad) + (pos >= 2 * n_pad) + (pos >= 3 * n_pad); };
+
     // lane owns V consecutive channels in each of NCH chunks of 32*V channels
     int grp[NCH];
 #pragma unroll
     for (int j = 0; j < NCH; ++j) grp[j] = ((j * 32 + lane) * V) / gd;
-    const int lpg = (gd / V) > 0 ? (gd / V) : 1;          // lanes per channel group (power of two, checked on the host)
+    const int lpg = gd / V;                               // lanes per channel group (power of two >= 4, host-checked)
     const char* fl = reinterpret_cast<const char*>(p.feat) + ((size_t)b * p.num_feat * p.C + (size_t)lane * V) * sizeof(T);
-    asm volatile("" : "+l"(fl));      // keep the lane's base in registers (nvcc otherwise re-derives it per item)
+    asm volatile("" : "+l"(fl));      // keep the lane's base in registers (nvcc otherwise re-derives it per quad)
+    const unsigned row_bytes = (unsigned)p.C * (unsigned)sizeof(T);
+    const float* w_unit = gc.weights + ((size_t)ba * NP + p0) * (L * G);     // weights of the unit's first pair
 
-    struct Item {
+    struct Rows {
         float v[4][kPacked ? 1 : NCH][kPacked ? 1 : V];
         uint4 raw[kPacked ? 4 : 1];
     };
-    auto issue = [&](int it, Item& r_) {
-        const uint4 rw = m_rows[it];
+    auto issue = [&](int qi, Rows& r_) {
+        const uint4 rw = q_rows[qi];
         const char* q1 = fl + rw.x;
         const char* q2 = fl + rw.y;
         const char* q3 = fl + rw.z;
@@ -240,7 +308,7 @@ __global__ void __launch_bounds__(kW * 32) dfa_group_kernel(const GroupParams p)
             }
         }
     };
-    auto corner = [&](const Item& r_, int k, int j, float (&vv)[V]) {
+    auto corner = [&](const Rows& r_, int k, int j, float (&vv)[V]) {
         if constexpr (kPacked) {
             unpack_bf16x8(r_.raw[k], vv);
         } else {
@@ -249,64 +317,187 @@ __global__ void __launch_bounds__(kW * 32) dfa_group_kernel(const GroupParams p)
         }
     };
 
-    if constexpr (!kBwd) {
-        float acc[NCH][V];
+    float acc[NCH][V];      // forward accumulators
+    float go[NCH][V];       // backward: grad_out of this row at the lane's channels
 #pragma unroll
-        for (int j = 0; j < NCH; ++j)
+    for (int j = 0; j < NCH; ++j)
 #pragma unroll
-            for (int e = 0; e < V; ++e) acc[j][e] = 0.f;
+        for (int e = 0; e < V; ++e) { acc[j][e] = 0.f; go[j][e] = 0.f; }
+    if (kBwd) {
+        const float* go_row = gc.grad_out + (size_t)b * gc.io_bstride + (size_t)a * p.C;
+#pragma unroll
+        for (int j = 0; j < NCH; ++j) VecIO<float, V>::load(go_row + (j * 32 + lane) * V, go[j]);
+    }
 
-        auto consume = [&](int it, const Item& r_) {
-            const float4 cf = m_coef[it];
-#pragma unroll
-            for (int j = 0; j < NCH; ++j) {
-                const float wj = m_w[it * kGroupMaxG + grp[j]];
-                const float kk[4] = {cf.x * wj, cf.y * wj, cf.z * wj, cf.w * wj};
-                float vv[4][V];
-#pragma unroll
-                for (int k = 0; k < 4; ++k) corner(r_, k, j, vv[k]);
-#pragma unroll
-                for (int e = 0; e < V; e += 2) {
-                    float2 a2 = make_float2(acc[j][e], acc[j][e + 1]);
-#pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        a2 = __ffma2_rn(make_float2(kk[k], kk[k]), make_float2(vv[k][e], vv[k][e + 1]), a2);
-                    acc[j][e] = a2.x;
-                    acc[j][e + 1] = a2.y;
+    for (int qc0 = 0; qc0 < n_quads; qc0 += kQuadChunk) {
+        const int nq = min(kQuadChunk, n_quads - qc0);
+
+        // -------------------------------------------------------------- phase 5: per-quad rows (+ forward tables)
+        for (int qi = tid; qi < nq; qi += kThreads) {
+            const int it = s_sorted[s_qstart[qc0 + qi]];         // first member: all members share the quad
+            const unsigned key = s_key[it];
+            const int cl = (int)(key >> 26) * L + level_of(it);
+            const int hl = (int)((key >> 13) & 8191u) - 1, wl = (int)(key & 8191u) - 1;
+            const int* t = tab + cl * 3;
+            const int w = t[1];
+            const int m = s_mask[it];
+            const int r1 = t[2] + hl * w + wl, r2 = r1 + 1, r3 = r1 + w, r4 = r3 + 1;
+            // out-of-bounds corners are redirected to an in-bounds corner of the same quad (their terms are 0)
+            const int safe = (m & 1) ? r1 : ((m & 2) ? r2 : ((m & 4) ? r3 : r4));
+            q_rows[qi] = make_uint4((unsigned)((m & 1) ? r1 : safe) * row_bytes, (unsigned)((m & 2) ? r2 : safe) * row_bytes,
+                                    (unsigned)((m & 4) ? r3 : safe) * row_bytes, (unsigned)((m & 8) ? r4 : safe) * row_bytes);
+        }
+        if constexpr (!kBwd) {
+            // table[quad][group] = sum over the quad's items of (bilinear term of corner k) * weight[group], k = 1..4
+            for (int task = tid; task < nq * G; task += kThreads) {
+                const int qi = task / G, g = task - qi * G;
+                const int r0 = s_qstart[qc0 + qi], r1 = s_qstart[qc0 + qi + 1];
+                float4 tsum = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int r = r0; r < r1; ++r) {
+                    const int it = s_sorted[r];
+                    const int l = level_of(it), i = it - l * n_pad;
+                    const float2 f = s_lhlw[it];
+                    const float hh = 1.f - f.x, hw = 1.f - f.y;          // same expressions as quad_setup()
+                    const int m = s_mask[it];
+                    const float wv = __ldg(w_unit + ((size_t)l_pair[i] * L + l) * G + g);
+                    tsum.x += ((m & 1) ? hh * hw : 0.f) * wv;
+                    tsum.y += ((m & 2) ? hh * f.y : 0.f) * wv;
+                    tsum.z += ((m & 4) ? f.x * hw : 0.f) * wv;
+                    tsum.w += ((m & 8) ? f.x * f.y : 0.f) * wv;
                 }
-            }
-        };
-        // items are dealt to the warps one by one; kDepth items in flight per warp
-        if constexpr (kPacked) {
-            Item I0, I1, I2, I3;
-            int it = warp;
-            if (it < n_items) issue(it, I0);
-            if (it + kW < n_items) issue(it + kW, I1);
-            if (it + 2 * kW < n_items) issue(it + 2 * kW, I2);
-            for (; it < n_items; it += 4 * kW) {
-                if (it + 3 * kW < n_items) issue(it + 3 * kW, I3);
-                consume(it, I0);
-                if (it + 4 * kW < n_items) issue(it + 4 * kW, I0);
-                if (it + kW < n_items) consume(it + kW, I1);
-                if (it + 5 * kW < n_items) issue(it + 5 * kW, I1);
-                if (it + 2 * kW < n_items) consume(it + 2 * kW, I2);
-                if (it + 6 * kW < n_items) issue(it + 6 * kW, I2);
-                if (it + 3 * kW < n_items) consume(it + 3 * kW, I3);
-            }
-        } else {
-            Item I0, I1;
-            int it = warp;
-            if (it < n_items) issue(it, I0);
-            for (; it < n_items; it += 2 * kW) {
-                const bool has1 = it + kW < n_items;
-                if (has1) issue(it + kW, I1);
-                consume(it, I0);
-                if (it + 2 * kW < n_items) issue(it + 2 * kW, I0);
-                if (has1) consume(it + kW, I1);
+                q_tab[qi * kGroupMaxG + g] = tsum;
             }
         }
+        __syncthreads();
 
-        // -------------------------------------------------------------- phase 4: cross-warp sum in warp order
+        // -------------------------------------------------------------- phase 6: gather, one distinct quad at a time
+        if constexpr (!kBwd) {
+            auto consume = [&](int qi, const Rows& r_) {
+#pragma unroll
+                for (int j = 0; j < NCH; ++j) {
+                    const float4 kk4 = q_tab[qi * kGroupMaxG + grp[j]];
+                    const float kk[4] = {kk4.x, kk4.y, kk4.z, kk4.w};
+                    float vv[4][V];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) corner(r_, k, j, vv[k]);
+#pragma unroll
+                    for (int e = 0; e < V; e += 2) {
+                        float2 a2 = make_float2(acc[j][e], acc[j][e + 1]);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            a2 = __ffma2_rn(make_float2(kk[k], kk[k]), make_float2(vv[k][e], vv[k][e + 1]), a2);
+                        acc[j][e] = a2.x;
+                        acc[j][e + 1] = a2.y;
+                    }
+                }
+            };
+            {
+                // quads are dealt to the warps one by one; kDepth quads in flight per warp (rotating register sets)
+                Rows I[kDepth];
+#pragma unroll
+                for (int d = 0; d + 1 < kDepth; ++d)
+                    if (warp + d * kW < nq) issue(warp + d * kW, I[d]);
+                for (int qi = warp; qi < nq; qi += kDepth * kW) {
+#pragma unroll
+                    for (int d = 0; d < kDepth; ++d) {
+                        const int qn = qi + (d + kDepth - 1) * kW;
+                        if (qn < nq) issue(qn, I[(d + kDepth - 1) % kDepth]);
+                        if (qi + d * kW < nq) consume(qi + d * kW, I[d]);
+                    }
+                }
+            }
+        } else {
+            // S[quad][group][k] = <grad_out, corner_k> over the channels of the group: per lane 4 partial dot products
+            // per chunk, reduced over the lpg lanes of the group by a transposing butterfly (each step halves the
+            // values a lane carries), the surviving lanes write one float each
+            auto consume = [&](int qi, const Rows& r_) {
+#pragma unroll
+                for (int j = 0; j < NCH; ++j) {
+                    float sk[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        float vv[V];
+                        corner(r_, k, j, vv);
+                        float2 s2 = make_float2(0.f, 0.f);
+#pragma unroll
+                        for (int e = 0; e < V; e += 2)
+                            s2 = __ffma2_rn(make_float2(go[j][e], go[j][e + 1]), make_float2(vv[e], vv[e + 1]), s2);
+                        sk[k] = s2.x + s2.y;
+                    }
+                    const int hA = lpg >> 1, hB = lpg >> 2;
+                    const bool upA = (lane & hA) != 0, upB = (lane & hB) != 0;
+                    // step A: lanes with bit hA clear keep corners {0,1}, the others {2,3}
+                    float a0 = upA ? sk[2] : sk[0], a1 = upA ? sk[3] : sk[1];
+                    const float s0 = upA ? sk[0] : sk[2], s1 = upA ? sk[1] : sk[3];
+                    a0 += __shfl_xor_sync(0xffffffffu, s0, hA);
+                    a1 += __shfl_xor_sync(0xffffffffu, s1, hA);
+                    // step B: bit hB clear keeps the first of the pair
+                    float v = upB ? a1 : a0;
+                    const float sb = upB ? a0 : a1;
+                    v += __shfl_xor_sync(0xffffffffu, sb, hB);
+                    for (int o = hB >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                    if ((lane & (hB - 1)) == 0) {
+                        const int k = (upA ? 2 : 0) + (upB ? 1 : 0);
+                        reinterpret_cast<float*>(q_tab + qi * kGroupMaxG + grp[j])[k] = v;
+                    }
+                }
+            };
+            {
+                // quads are dealt to the warps one by one; kDepth quads in flight per warp (rotating register sets)
+                Rows I[kDepth];
+#pragma unroll
+                for (int d = 0; d + 1 < kDepth; ++d)
+                    if (warp + d * kW < nq) issue(warp + d * kW, I[d]);
+                for (int qi = warp; qi < nq; qi += kDepth * kW) {
+#pragma unroll
+                    for (int d = 0; d < kDepth; ++d) {
+                        const int qn = qi + (d + kDepth - 1) * kW;
+                        if (qn < nq) issue(qn, I[(d + kDepth - 1) % kDepth]);
+                        if (qi + d * kW < nq) consume(qi + d * kW, I[d]);
+                    }
+                }
+            }
+            __syncthreads();
+
+            // ---------------------------------------------------------- phase 7 (backward): one thread per item
+            // g_w[item][g] = sum_k c_k S[g][k];  location-gradient terms of the item = sum_g w[g] * (dx . S[g], dy . S[g])
+            // (cu:86-125: d/dx = W (-hh v1 + hh v2 - lh v3 + lh v4), d/dy = H (-hw v1 - lw v2 + hw v3 + lw v4))
+            const int ra = s_qstart[qc0], rb = s_qstart[qc0 + nq];
+            for (int r = ra + tid; r < rb; r += kThreads) {
+                const int it = s_sorted[r];
+                const int l = level_of(it), i = it - l * n_pad;
+                const int qi = (int)s_qof[it] - qc0;
+                const int* t = tab + ((int)(s_key[it] >> 26) * L + l) * 3;
+                const float2 f = s_lhlw[it];
+                ItemGeo ig;
+                ig.lh = f.x; ig.lw = f.y; ig.hh = 1.f - f.x; ig.hw = 1.f - f.y;   // same expressions as quad_setup()
+                const int m = s_mask[it];
+                const float W_ = (float)t[1], H_ = (float)t[0];
+                const float c1 = (m & 1) ? ig.hh * ig.hw : 0.f, c2 = (m & 2) ? ig.hh * ig.lw : 0.f;
+                const float c3 = (m & 4) ? ig.lh * ig.hw : 0.f, c4 = (m & 8) ? ig.lh * ig.lw : 0.f;
+                const float x1 = (m & 1) ? -ig.hh * W_ : 0.f, x2 = (m & 2) ? ig.hh * W_ : 0.f;
+                const float x3 = (m & 4) ? -ig.lh * W_ : 0.f, x4 = (m & 8) ? ig.lh * W_ : 0.f;
+                const float y1 = (m & 1) ? -ig.hw * H_ : 0.f, y2 = (m & 2) ? -ig.lw * H_ : 0.f;
+                const float y3 = (m & 4) ? ig.hw * H_ : 0.f, y4 = (m & 8) ? ig.lw * H_ : 0.f;
+                const size_t woff = ((size_t)l_pair[i] * L + l) * G;
+                const float* wsrc = w_unit + woff;
+                float* gdst = gc.g_w + ((size_t)ba * NP + p0) * (L * G) + woff;
+                float gx = 0.f, gy = 0.f;
+                for (int g = 0; g < G; ++g) {
+                    const float4 s4 = q_tab[qi * kGroupMaxG + g];
+                    const float wv = __ldg(wsrc + g);
+                    gdst[g] = c1 * s4.x + c2 * s4.y + c3 * s4.z + c4 * s4.w;
+                    gx = __fmaf_rn(x1 * s4.x + x2 * s4.y + x3 * s4.z + x4 * s4.w, wv, gx);
+                    gy = __fmaf_rn(y1 * s4.x + y2 * s4.y + y3 * s4.z + y4 * s4.w, wv, gy);
+                }
+                s_gxy[it] = make_float2(gx, gy);
+            }
+        }
+        __syncthreads();      // the quad tables are rewritten by the next chunk / reused as reduction scratch
+    }
+
+    if constexpr (!kBwd) {
+        // -------------------------------------------------------------- phase 8: cross-warp sum in warp order
 #pragma unroll
         for (int j = 0; j < NCH; ++j)
 #pragma unroll
@@ -344,115 +535,11 @@ __global__ void __launch_bounds__(kW * 32) dfa_group_kernel(const GroupParams p)
             }
         }
     } else {
-        // -------------------------------------------------------------- backward: g_w per item, g_loc per pair
-        float go[NCH][V];
-        {
-            const float* go_row = gc.grad_out + (size_t)b * gc.io_bstride + (size_t)a * p.C;
-#pragma unroll
-            for (int j = 0; j < NCH; ++j) VecIO<float, V>::load(go_row + (j * 32 + lane) * V, go[j]);
-        }
-        float* const gw_block = gc.g_w + (size_t)ba * NP * (L * G);
-        float2* const gloc_row = reinterpret_cast<float2*>(gc.g_loc) + (size_t)ba * NP;
-        float gx = 0.f, gy = 0.f;
-
-        auto consume = [&](int it, const Item& r_) {
-            const float4 cf = m_coef[it], cx4 = m_dx[it], cy4 = m_dy[it];
-            const float cc[4] = {cf.x, cf.y, cf.z, cf.w};
-            const float ax[4] = {cx4.x, cx4.y, cx4.z, cx4.w};
-            const float by[4] = {cy4.x, cy4.y, cy4.z, cy4.w};
-            const int pair = p0 + l_pair[it >> 2];
-            float* gw_dst = gw_block + ((size_t)pair * L + (it & 3)) * G;
-            float gwv[NCH];
-#pragma unroll
-            for (int j = 0; j < NCH; ++j) {
-                float sk[4];
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    float vv[V];
-                    corner(r_, k, j, vv);
-                    float2 s2 = make_float2(0.f, 0.f);
-#pragma unroll
-                    for (int e = 0; e < V; e += 2)
-                        s2 = __ffma2_rn(make_float2(go[j][e], go[j][e + 1]), make_float2(vv[e], vv[e + 1]), s2);
-                    sk[k] = s2.x + s2.y;
-                }
-                const float wj = m_w[it * kGroupMaxG + grp[j]];
-                gwv[j] = cc[0] * sk[0] + cc[1] * sk[1] + cc[2] * sk[2] + cc[3] * sk[3];
-                const float dxs = ax[0] * sk[0] + ax[1] * sk[1] + ax[2] * sk[2] + ax[3] * sk[3];
-                const float dys = by[0] * sk[0] + by[1] * sk[1] + by[2] * sk[2] + by[3] * sk[3];
-                gx = __fmaf_rn(dxs, wj, gx);
-                gy = __fmaf_rn(dys, wj, gy);
-            }
-            // weight gradient: sum over the lpg lanes of each channel group, one store per group
-            if constexpr (NCH == 2) {
-                if (lpg >= 2) {
-                    // two group sums per lane: the first butterfly step also splits them between the halves
-                    const int half = lpg >> 1;
-                    const bool up = (lane & half) != 0;
-                    const float send = up ? gwv[0] : gwv[1];
-                    float keep = up ? gwv[1] : gwv[0];
-                    keep += __shfl_xor_sync(0xffffffffu, send, half);
-#pragma unroll
-                    for (int o = 8; o > 0; o >>= 1)
-                        if (o < half) keep += __shfl_xor_sync(0xffffffffu, keep, o);
-                    const int sub = lane & (lpg - 1);
-                    if (sub == 0) gw_dst[grp[0]] = keep;
-                    if (sub == half) gw_dst[grp[1]] = keep;
-                } else {
-                    gw_dst[grp[0]] = gwv[0];
-                    gw_dst[grp[1]] = gwv[1];
-                }
-            } else {
-#pragma unroll
-                for (int j = 0; j < NCH; ++j) {
-                    float gw = gwv[j];
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1)
-                        if (o < lpg) gw += __shfl_xor_sync(0xffffffffu, gw, o);
-                    if ((lane & (lpg - 1)) == 0) gw_dst[grp[j]] = gw;
-                }
-            }
-            if ((it & 3) == L - 1) {
-                // last level of the pair: gx and gy reduced together (lower half-warp ends with gx, upper with gy)
-                const bool up = (lane & 16) != 0;
-                const float send = up ? gx : gy;
-                float keep = up ? gy : gx;
-                keep += __shfl_xor_sync(0xffffffffu, send, 16);
-#pragma unroll
-                for (int o = 8; o > 0; o >>= 1) keep += __shfl_xor_sync(0xffffffffu, keep, o);
-                if ((lane & 15) == 0) reinterpret_cast<float*>(gloc_row + pair)[up ? 1 : 0] = keep;
-                gx = 0.f;
-                gy = 0.f;
-            }
-        };
-        // warp `warp` owns visible pairs warp, warp+kW, ... and walks their 4 levels back to back
-        const int my_pairs = (n_list > warp) ? (n_list - warp + kW - 1) / kW : 0;
-        const int my_items = my_pairs * L;
-        auto item_of = [&](int q) { return ((warp + (q >> 2) * kW) << 2) + (q & 3); };
-        if constexpr (kPacked) {
-            Item I0, I1, I2, I3;
-            if (my_items > 0) issue(item_of(0), I0);
-            if (my_items > 1) issue(item_of(1), I1);
-            if (my_items > 2) issue(item_of(2), I2);
-            for (int q = 0; q < my_items; q += 4) {      // my_items is a multiple of 4
-                issue(item_of(q + 3), I3);
-                consume(item_of(q), I0);
-                if (q + 4 < my_items) issue(item_of(q + 4), I0);
-                consume(item_of(q + 1), I1);
-                if (q + 5 < my_items) issue(item_of(q + 5), I1);
-                consume(item_of(q + 2), I2);
-                if (q + 6 < my_items) issue(item_of(q + 6), I2);
-                consume(item_of(q + 3), I3);
-            }
-        } else {
-            Item I0, I1;
-            if (my_items > 0) issue(item_of(0), I0);
-            for (int q = 0; q < my_items; q += 2) {      // my_items is a multiple of 4
-                issue(item_of(q + 1), I1);
-                consume(item_of(q), I0);
-                if (q + 2 < my_items) issue(item_of(q + 2), I0);
-                consume(item_of(q + 1), I1);
-            }
+        // -------------------------------------------------------------- phase 8 (backward): location gradient per pair
+        float2* const gloc = reinterpret_cast<float2*>(gc.g_loc) + (size_t)ba * NP + p0;
+        for (int i = tid; i < n_list; i += kThreads) {
+            const float2 t0 = s_gxy[i], t1 = s_gxy[n_pad + i], t2 = s_gxy[2 * n_pad + i], t3 = s_gxy[3 * n_pad + i];
+            gloc[l_pair[i]] = make_float2(((t0.x + t1.x) + t2.x) + t3.x, ((t0.y + t1.y) + t2.y) + t3.y);
         }
     }
 }

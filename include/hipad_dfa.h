@@ -196,6 +196,17 @@ int hipad_dfa_group_backward(int feat_is_bf16, int grad_feat_flags, const void *
                              int num_scale, int num_groups,
                              void *workspace, size_t workspace_bytes, void *stream);
 
+/* Measurement variant of hipad_dfa_group_backward: runs only the kernels selected by stage_mask (bit0 sample-major
+ * kernel + zero fill, bit1 compaction + sort, bit2 classification + reduce, bit3 zero fill as its own kernel), like
+ * hipad_dfa_backward_stages.  grad_mc_ms_feat must not be NULL. */
+int hipad_dfa_group_backward_stages(int feat_is_bf16, int grad_feat_flags, int stage_mask, const void *mc_ms_feat,
+                                    const int32_t *spatial_shape, const int32_t *scale_start_index,
+                                    const hipad_dfa_call_t *calls, int num_calls,
+                                    const float *grad_output_packed, void *grad_mc_ms_feat,
+                                    int batch_size, int num_cams, int num_feat, int num_embeds,
+                                    int num_scale, int num_groups,
+                                    void *workspace, size_t workspace_bytes, void *stream);
+
 /* Debugging: byte offset of the backward's 8 work counters inside its workspace (part items, -, partial slots used,
  * tiny rows, reduce queue head, ...). */
 size_t hipad_dfa_debug_counters_offset(int batch_size, int num_cams, int num_feat, int num_embeds,

@@ -109,6 +109,17 @@ res["layer"] = {"fwd_sum_legacy_us": round(sum(res[c["kind"]]["fwd_legacy_us"] f
                 "fwd_grouped_us": timed(lambda: fwd_group(calls, out_packed, wf_all)),
                 "bwd_grouped_us": timed(lambda: bwd_group(calls, go_packed, wb_all)),
                 "bwd_grouped_accumulate_us": timed(lambda: bwd_group(calls, go_packed, wb_all, flags=1))}
+def bwd_stage(mask):
+    t, tp = table(calls, True)
+    _lib.check(lib.hipad_dfa_group_backward_stages(int(bf16), 0, mask, feat.data_ptr(), sh.data_ptr(), st.data_ptr(), tp, len(calls),
+                                                   go_packed.data_ptr(), g_feat.data_ptr(), bs, CAMS, F, C, L, G, wb_all.data_ptr(),
+                                                   wb_all.numel(), stream), "group bwd stage")
+
+
+bwd_group(calls, go_packed, wb_all)      # workspace holds a complete chain result for the isolated stages
+res["layer"]["bwd_grouped_stage_us"] = {"sample+zero": timed(lambda: bwd_stage(1)), "compact+sort": timed(lambda: bwd_stage(2)),
+                                        "classify+reduce": timed(lambda: bwd_stage(4)),
+                                        "serial_all": timed(lambda: [bwd_stage(1), bwd_stage(2), bwd_stage(4)])}
 # serial 4-call layer through one stream (what the public per-call API does)
 res["layer"]["fwd_serial4_legacy_us"] = timed(lambda: [fwd_legacy(c) for c in calls])
 res["layer"]["fwd_serial4_group1_us"] = timed(lambda: [fwd_group([c], c["out"], wf[c["kind"]]) for c in calls])
