@@ -184,7 +184,17 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------- GPU arm
+WORKLOAD = ("HiP-AD stage-2 decoder DFA path: 6 layers x (det 900x13 + map 100x300 + plan 480x90 + ego 1x13), "
+            "6 cams, 4 levels of 352x640, C=256, G=8, fwd+bwd")
+
+
+def shared_config(bs, dtype):
+    """`config` of BOTH arms (the driver compares them): what the workload is, nothing about how it is run."""
+    return {"workload": WORKLOAD, "bs_per_gpu": bs, "feature_dtype": dtype}
+
+
 def gpu_arm(args):
+    import ctypes
     import torch.distributed as dist
     import hipad_b200
     from hipad_b200 import _lib
@@ -213,14 +223,9 @@ def gpu_arm(args):
     shapes_d = torch.from_numpy(shapes).to(dev)
     starts_d = torch.from_numpy(starts).to(dev)
     dims = lambda c: (bs, CAMS, F, C, L, c["A"], c["P"], G)
-    ws_bytes = max(lib.hipad_dfa_backward_workspace_bytes(*dims(c)) for c in calls)
-    # One workspace and one dense g_feat buffer per MODALITY (reused across layers, written in full by every call):
-    # the four calls of a decoder layer are independent, so with --streams 4 they run as parallel graph branches.
-    n_lanes = 1 if args.streams <= 1 else len(MODALITIES)
-    ws_l = [torch.empty(ws_bytes, dtype=torch.uint8, device=dev) for _ in range(n_lanes)]
-    g_feat_l = [torch.empty_like(feat) for _ in range(n_lanes)]
+    n_mod = len(MODALITIES)
+    n_lanes = 1 if args.streams <= 1 else n_mod
     lane_of = {m[0]: (i % n_lanes) for i, m in enumerate(MODALITIES)}
-    ws, g_feat = ws_l[0], g_feat_l[0]
     total_fwd = total_bwd = 0
     for c in calls:
         c["loc_d"] = torch.from_numpy(c["loc"]).to(dev)
@@ -233,19 +238,43 @@ def gpu_arm(args):
         total_fwd += c["bytes"]["fwd"]
         total_bwd += c["bytes"]["bwd"]
     step_bytes = total_fwd + total_bwd
+    dense = bs * F * C * elem
+    layers = [calls[i:i + n_mod] for i in range(0, len(calls), n_mod)]
 
-    fwd_fn = lib.hipad_dfa_forward_bf16 if bf16 else lib.hipad_dfa_forward_f32
+    def table(cs, bwd):
+        t = _lib.call_table([(c["loc_d"].data_ptr(), c["w_d"].data_ptr(), c["g_loc_d"].data_ptr() if bwd else None,
+                              c["g_w_d"].data_ptr() if bwd else None, c["A"], c["P"]) for c in cs])
+        return t, ctypes.cast(t, ctypes.c_void_p)
+
+    def fwd_ws_bytes(cs):
+        _, tp = table(cs, False)
+        return max(256, lib.hipad_dfa_group_forward_workspace_bytes(tp, len(cs), bs, CAMS, C))
+
+    def bwd_ws_bytes(cs):
+        _, tp = table(cs, True)
+        return max(256, lib.hipad_dfa_group_backward_workspace_bytes(tp, len(cs), bs, CAMS, F, C, L, G))
+
+    # ---- per-call step (the reference's own contract: 24 calls, each with its own dense feature gradient).  One
+    # forward / backward workspace and one dense g_feat per MODALITY (reused across layers, written in full by every
+    # call): the four calls of a decoder layer are independent, so with --streams 4 they run as parallel graph branches.
+    ws_f = [torch.empty(max(fwd_ws_bytes([c]) for c in calls), dtype=torch.uint8, device=dev) for _ in range(n_lanes)]
+    ws_b = [torch.empty(max(bwd_ws_bytes([c]) for c in calls), dtype=torch.uint8, device=dev) for _ in range(n_lanes)]
+    g_feat_l = [torch.empty_like(feat) for _ in range(n_lanes)]
 
     def fwd_call(c, stream):
-        _lib.check(fwd_fn(c["out_d"].data_ptr(), feat.data_ptr(), shapes_d.data_ptr(), starts_d.data_ptr(),
-                          c["loc_d"].data_ptr(), c["w_d"].data_ptr(), *dims(c), stream), "forward")
+        lane = lane_of[c["kind"]]
+        _, tp = table([c], False)
+        _lib.check(lib.hipad_dfa_group_forward(int(bf16), c["out_d"].data_ptr(), feat.data_ptr(), shapes_d.data_ptr(),
+                                               starts_d.data_ptr(), tp, 1, bs, CAMS, F, C, L, G, ws_f[lane].data_ptr(),
+                                               ws_f[lane].numel(), stream), "forward")
 
     def bwd_call(c, stream, mask=7):
         lane = lane_of[c["kind"]]
         _lib.check(lib.hipad_dfa_backward_stages(
             1 if bf16 else 0, mask, feat.data_ptr(), shapes_d.data_ptr(), starts_d.data_ptr(),
             c["loc_d"].data_ptr(), c["w_d"].data_ptr(), c["go_d"].data_ptr(), g_feat_l[lane].data_ptr(),
-            c["g_loc_d"].data_ptr(), c["g_w_d"].data_ptr(), *dims(c), ws_l[lane].data_ptr(), ws_bytes, stream), "backward")
+            c["g_loc_d"].data_ptr(), c["g_w_d"].data_ptr(), *dims(c), ws_b[lane].data_ptr(), ws_b[lane].numel(), stream),
+            "backward")
 
     side = [torch.cuda.Stream(device=dev) for _ in range(n_lanes - 1)]
 
@@ -272,89 +301,137 @@ def gpu_arm(args):
         for ev in joins:
             main.wait_event(ev)
 
-    n_mod = len(MODALITIES)
-    layers = [calls[i:i + n_mod] for i in range(0, len(calls), n_mod)]
-
     def issue_step(main):
         for group in layers:                    # decoder forward: 6 layers x 4 modalities
             layer_group(group, fwd_call, main)
         for group in reversed(layers):          # autograd order
             layer_group(list(reversed(group)), bwd_call, main)
 
-    def issue_step_shared(main):
-        # "next" row f1: ONE dense g_feat for the whole step (all 24 calls read the same feature tensor): the first
-        # backward call writes every row, the others accumulate (hipad_dfa_backward_accumulate_*), serial on `main`
-        for group in layers:
-            layer_group(group, fwd_call, main)
-        first = True
-        for c in reversed(calls):
-            _lib.check(lib.hipad_dfa_backward_stages(
-                1 if bf16 else 0, 7 if first else 7 | 32, feat.data_ptr(), shapes_d.data_ptr(), starts_d.data_ptr(),
-                c["loc_d"].data_ptr(), c["w_d"].data_ptr(), c["go_d"].data_ptr(), g_feat_l[0].data_ptr(),
-                c["g_loc_d"].data_ptr(), c["g_w_d"].data_ptr(), *dims(c), ws_l[0].data_ptr(), ws_bytes, main.cuda_stream),
-                "backward (shared g_feat)")
-            first = False
+    # ---- grouped step ("next" row f1): ONE launch per decoder layer forward, ONE backward chain per layer, ONE dense
+    # fp32 feature gradient for the whole step (first layer of the backward writes it, the others accumulate)
+    a_total = sum(c["A"] for c in layers[0])
+    for li, group in enumerate(layers):
+        out_p = torch.empty((bs, a_total, C), dtype=torch.float32, device=dev)
+        go_p = torch.cat([c["go_d"] for c in group], dim=1).contiguous()
+        for c in group:
+            c["out_p"], c["go_p"] = out_p, go_p
+    ws_fg = torch.empty(fwd_ws_bytes(layers[0]), dtype=torch.uint8, device=dev)
+    ws_bg = torch.empty(bwd_ws_bytes(layers[0]), dtype=torch.uint8, device=dev)
+    g_feat_step = torch.empty((bs, F, C), dtype=torch.float32, device=dev)
 
-    # per call: forward sample kernel; backward = sample kernel (+ its own zero-fill kernel when the grid is too
-    # small to fold the fill in: the ego call), visible compaction, band sort, row classification, reduce
-    # (stage label "dfa_gfeat_rows+heavy" = classification + reduce kernels)
-    launches_per_step = sum(1 + 5 + (1 if bs * c["A"] * 8 < 2 * 148 else 0) for c in calls)
+    def group_fwd(group, stream):
+        _, tp = table(group, False)
+        _lib.check(lib.hipad_dfa_group_forward(int(bf16), group[0]["out_p"].data_ptr(), feat.data_ptr(), shapes_d.data_ptr(),
+                                               starts_d.data_ptr(), tp, len(group), bs, CAMS, F, C, L, G, ws_fg.data_ptr(),
+                                               ws_fg.numel(), stream), "group forward")
+
+    def group_bwd(group, stream, flags, mask=7):
+        _, tp = table(group, True)
+        _lib.check(lib.hipad_dfa_group_backward_stages(int(bf16), flags, mask, feat.data_ptr(), shapes_d.data_ptr(),
+                                                       starts_d.data_ptr(), tp, len(group), group[0]["go_p"].data_ptr(),
+                                                       g_feat_step.data_ptr(), bs, CAMS, F, C, L, G, ws_bg.data_ptr(),
+                                                       ws_bg.numel(), stream), "group backward")
+
+    def issue_group_step(main):
+        for group in layers:
+            group_fwd(group, main.cuda_stream)
+        for i, group in enumerate(reversed(layers)):
+            group_bwd(group, main.cuda_stream, 2 if i == 0 else 3)
+
+    # launches per step: per call 1 forward (+1 ticket memset when rows are sliced: map, plan) and 5 backward kernels
+    # (+1 zero-fill kernel when the grid is too small to fold the fill in: the ego call)
+    def sliced(c):
+        return c["P"] * CAMS > 96
+    launches_per_step = sum(1 + (1 if sliced(c) else 0) + 5 + (1 if bs * c["A"] * max(1, -(-c["P"] * CAMS // 96)) < 2 * 148 else 0)
+                            for c in calls)
+    launches_group_step = len(layers) * (2 + 5)
     flush = torch.zeros(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
     def flush_l2():
         # read-only sweep of 256 MiB: evicts everything, leaves only clean lines behind
         return flush.view(torch.int64).sum()
 
-    # ---- capture one step as a CUDA graph (launch-bound at bs=1 otherwise)
     stream = torch.cuda.Stream(device=dev)
-    graph = None
-    with torch.cuda.stream(stream):
-        issue_step(stream)
-        torch.cuda.synchronize()
-        if not args.no_graph:
+
+    def capture(issue):
+        with torch.cuda.stream(stream):
+            issue(stream)
+            torch.cuda.synchronize()
+            if args.no_graph:
+                return None
             try:
-                graph = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(graph, stream=stream):
-                    issue_step(torch.cuda.current_stream())
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=stream):
+                    issue(torch.cuda.current_stream())
+                return g
             except Exception as e:  # keep measuring, eagerly
                 print("graph capture failed, timing eager launches:", e, file=sys.stderr)
-                graph = None
-    torch.cuda.synchronize()
-
-    def run_step():
-        if graph is not None:
-            graph.replay()
-        else:
-            issue_step(torch.cuda.current_stream())
+                return None
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    with torch.cuda.stream(stream):
-        for _ in range(max(args.warmup, 3)):
-            flush_l2()
-            run_step()
-        barrier()
-        sampler = ClockSampler(local_rank)
-        if rank == 0:
-            sampler.start()
-        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-        barrier()
-        for a, b in ev:
-            flush_l2()                  # L2 flush between timed iterations (outside the timed interval)
-            a.record()
-            run_step()
-            b.record()
-        barrier()
-        step_ms = [a.elapsed_time(b) for a, b in ev]
-        clocks = sampler.stop() if rank == 0 else None
-    total_ms = max_over_ranks(float(sum(step_ms)), dev)
-    ms_per_step = total_ms / args.steps
+    def timed_steps(graph, issue, steps, warmup, sample_clocks=False):
+        with torch.cuda.stream(stream):
+            def run():
+                if graph is not None:
+                    graph.replay()
+                else:
+                    issue(torch.cuda.current_stream())
+            for _ in range(max(warmup, 3)):
+                flush_l2()
+                run()
+            barrier()
+            sampler = ClockSampler(local_rank) if (sample_clocks and rank == 0) else None
+            if sampler:
+                sampler.start()
+            ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+            barrier()
+            for a, b in ev:
+                flush_l2()                  # L2 flush between timed iterations (outside the timed interval)
+                a.record()
+                run()
+                b.record()
+            barrier()
+            total = float(sum(a.elapsed_time(b) for a, b in ev))
+            clocks = sampler.stop() if sampler else None
+        return max_over_ranks(total, dev) / steps, clocks
+
+    graph = capture(issue_step)
+    torch.cuda.synchronize()
+    ms_per_step, clocks = timed_steps(graph, issue_step, args.steps, args.warmup, sample_clocks=True)
     value = whole_job_gbs(world, step_bytes, ms_per_step)
 
-    # ---- BASELINE configs[1]: decoder FORWARD at bs-per-GPU inference, every DFA call through the fused kernel
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "6650 GB/s (of fallback)"
+
+    # ---- grouped step
+    group_step = None
+    try:
+        g2 = capture(issue_group_step)
+        ms2, _ = timed_steps(g2, issue_group_step, args.steps, 3)
+        # bytes the grouped step has to move: everything of the per-call step except 23 of the 24 dense g_feat writes
+        # (one fp32 buffer for the step; the read-modify-write of touched rows by later layers is not counted)
+        bytes2 = step_bytes - len(calls) * dense + bs * F * C * 4
+        group_step = {"ms_per_step": round(ms2, 4), "samples_per_s": round(world * bs / (ms2 * 1e-3), 1),
+                      "algorithmic_bytes_per_step": int(bytes2), "value": round(whole_job_gbs(world, bytes2, ms2), 2),
+                      "unit": "GB/s", "frac_of_peak": round(whole_job_gbs(1, bytes2, ms2) / peak, 4),
+                      "gpu_launches_per_step": launches_group_step,
+                      "speedup_vs_per_call_step": round(ms_per_step / ms2, 3),
+                      "note": "hipad_dfa_group_forward / _backward: one launch per decoder layer forward, one backward chain per "
+                              "layer, ONE dense fp32 feature gradient per step (zero-filled once, later layers accumulate); one "
+                              "stream, one CUDA graph; same outputs and gradients as the 24 calls (sum of their g_feat)"}
+    except Exception as e:
+        group_step = {"error": str(e)[:200]}
+
+    # ---- BASELINE configs[1], kernel-only view: every DFA call of a decoder forward through the fused kernel
     # (key-point projection + group softmax + aggregation in one launch, raw weights_fc logits in)
     inference = None
     if not args.no_graph:
@@ -375,55 +452,19 @@ def gpu_arm(args):
                 for group in layers:
                     layer_group(group, fused_call, main)
 
-            with torch.cuda.stream(stream):
-                issue_inference(stream)
-                torch.cuda.synchronize()
-                g3 = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g3, stream=stream):
-                    issue_inference(torch.cuda.current_stream())
-                for _ in range(3):
-                    flush_l2(); g3.replay()
-                ev3 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-                for a, b in ev3:
-                    flush_l2(); a.record(); g3.replay(); b.record()
-                torch.cuda.synchronize()
-            ms3 = max_over_ranks(float(sum(a.elapsed_time(b) for a, b in ev3)), dev) / args.steps
-            inference = {"ms_per_forward": round(ms3, 4), "samples_per_s": round(world * bs / (ms3 * 1e-3), 1),
-                         "note": "24 fused DFA calls of one stage-2 decoder forward (projection + softmax + aggregation "
-                                 "per launch), one CUDA graph, L2 flushed between replays"}
+            g3 = capture(issue_inference)
+            ms3, _ = timed_steps(g3, issue_inference, args.steps, 3)
+            inference = {"ms_per_forward": round(ms3, 4), "dfa_only_samples_per_s": round(world * bs / (ms3 * 1e-3), 1),
+                         "note": "the 24 DFA calls of one stage-2 decoder forward through the fused kernel (projection + softmax + "
+                                 "aggregation per launch), one CUDA graph, L2 flushed between replays; the decoder itself is "
+                                 "measured in `decoder_forward`"}
         except Exception as e:
             inference = {"error": str(e)[:200]}
 
-    # ---- same step with one shared g_feat buffer (reported beside the headline, never instead of it)
-    shared = None
-    if not args.no_graph:
-        try:
-            with torch.cuda.stream(stream):
-                issue_step_shared(stream)
-                torch.cuda.synchronize()
-                g2 = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g2, stream=stream):
-                    issue_step_shared(torch.cuda.current_stream())
-                for _ in range(3):
-                    flush_l2(); g2.replay()
-                ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-                for a, b in ev2:
-                    flush_l2(); a.record(); g2.replay(); b.record()
-                torch.cuda.synchronize()
-            ms2 = max_over_ranks(float(sum(a.elapsed_time(b) for a, b in ev2)), dev) / args.steps
-            dense = bs * F * C * elem
-            touched = sum(c["bytes"]["U"] * C * elem for c in calls)
-            bytes2 = step_bytes - (len(calls) - 1) * dense + 2 * (touched - calls[-1]["bytes"]["U"] * C * elem)
-            shared = {"ms_per_step": round(ms2, 4), "algorithmic_bytes_per_step": int(bytes2),
-                      "value": round(whole_job_gbs(world, bytes2, ms2), 2), "unit": "GB/s",
-                      "note": "one dense g_feat per step: 1 full write + read-modify-write of the touched rows of the other 23 calls"}
-        except Exception as e:
-            shared = {"error": str(e)[:200]}
-
-    # ---- per-kernel timing (CUDA events on the launching stream), for the roofline object
-    kern = {"dfa_sample_kernel<fwd>": [], "dfa_sample_kernel<bwd>+zero_fill": [], "dfa_vis_compact+band_sort": [],
-            "dfa_gfeat_rows+heavy": []}
-    kbytes = {k: [] for k in kern}
+    # ---- per-kernel timing (CUDA events on the launching stream), for the roofline objects
+    names = ["forward sample kernel", "backward sample kernel + zero fill", "compaction + band sort", "classify + reduce"]
+    kern = {k: [] for k in names}
+    kbytes = {k: [] for k in names}
     per_mod = {}
     with torch.cuda.stream(stream):
         s = stream.cuda_stream
@@ -446,37 +487,52 @@ def gpu_arm(args):
                 # everything of B_bwd except the touched rows of the dense g_feat write (it zero-fills the rest);
                 # the reduce writes those touched rows; the sort only re-reads locations (no algorithmic bytes)
                 touched = c["bytes"]["U"] * C * elem
-                for name, dur, nb in zip(kern, d, (c["bytes"]["fwd"], c["bytes"]["bwd"] - touched, 0, touched)):
+                for name, dur, nb in zip(names, d, (c["bytes"]["fwd"], c["bytes"]["bwd"] - touched, 0, touched)):
                     kern[name].append(dur)
                     kbytes[name].append(nb)
                 m = per_mod.setdefault(c["kind"], dict(fwd_us=[], bwd_us=[], bytes=c["bytes"]))
                 m["fwd_us"].append(d[0]); m["bwd_us"].append(d[1] + d[2] + d[3])
+        # the grouped layer, stage by stage
+        gl = {"forward (1 launch)": [], "backward sample kernel + zero fill": [], "compaction + band sort": [],
+              "classify + reduce": []}
+        for rep in range(3):
+            for group in layers[:2]:
+                flush_l2()
+                e = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+                e[0].record(); group_fwd(group, s); e[1].record()
+                group_bwd(group, s, 2, 1); e[2].record()
+                group_bwd(group, s, 2, 2); e[3].record()
+                group_bwd(group, s, 2, 4); e[4].record()
+                stream.synchronize()
+                if rep:
+                    for k, i in zip(gl, range(4)):
+                        gl[k].append(e[i].elapsed_time(e[i + 1]) * 1e3)
     share = {k: float(np.sum(v)) for k, v in kern.items()}
+    per_kernel = []
+    for k in names:
+        us = float(np.mean(kern[k])); nb = float(np.mean(kbytes[k]))
+        per_kernel.append({"kernel": k, "avg_launch_us": round(us, 2), "algorithmic_bytes_per_launch": int(nb),
+                           "achieved_gbs": round(nb / (us * 1e-6) / 1e9, 1), "frac": round(nb / (us * 1e-6) / 1e9 / peak, 4),
+                           "share_of_step": round(share[k] / max(sum(share.values()), 1e-9), 3)})
     dominant = max((k for k in share if np.sum(kbytes[k]) > 0), key=share.get)
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    peak = float(peaks.get("hbm_gbs", 6650.0))
-    peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "6650 GB/s (of fallback)"
-    dom_us = float(np.mean(kern[dominant]))
-    dom_bytes = float(np.mean(kbytes[dominant]))
-    achieved = dom_bytes / (dom_us * 1e-6) / 1e9
+    dom = next(p_ for p_ in per_kernel if p_["kernel"] == dominant)
     traffic = None
-    try:   # dram bytes per launch of the dominant kernel from the committed ncu capture, if any
+    try:   # dram bytes per launch of the dominant kernel from the committed ncu capture (profiles/ncu_traffic.py), if any
         traffic = json.load(open(os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json"))).get(dominant)
     except Exception:
         pass
-    roofline = {"bound": "hbm", "kernel": dominant, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
-                "avg_launch_us": round(dom_us, 2), "algorithmic_bytes_per_launch": int(dom_bytes),
-                "kernel_share_of_step": {k: round(v / max(sum(share.values()), 1e-9), 3) for k, v in share.items()},
-                "step_frac_of_peak": round(value / world / peak, 4)}
+    zero_fill_bytes = len(calls) * dense
+    roofline = {"bound": "hbm", "kernel": dominant, "achieved": dom["achieved_gbs"], "peak": peak, "unit": "GB/s",
+                "frac": dom["frac"], "traffic": traffic, "peak_source": peak_src,
+                "avg_launch_us": dom["avg_launch_us"], "algorithmic_bytes_per_launch": dom["algorithmic_bytes_per_launch"],
+                "step_frac_of_peak": round(value / world / peak, 4),
+                "step_frac_excluding_zero_fill": round(whole_job_gbs(1, step_bytes - zero_fill_bytes, ms_per_step) / peak, 4),
+                "note": "per-call step: 24 dense g_feat zero fills are %d of the %d algorithmic bytes" % (zero_fill_bytes, step_bytes)}
+    grouped_layer_us = {k: round(float(np.mean(v)), 1) for k, v in gl.items() if v}
 
     # ---- reference CUDA op (oracle/_ref, rebuilt from the reference sources) on the same inputs
     ref_cuda = None
-    if not bf16:
+    if not bf16 and not args.skip_ref_op:
         try:
             from oracle import build_ref
             if build_ref.available():
@@ -495,9 +551,9 @@ def gpu_arm(args):
                         ext.deformable_aggregation_forward(rf, shapes_d, starts_d, c["loc_d"], c["w_d"])
                     e1.record()
                     for _ in range(n):
-                        gf, gl, gw = z(rf), z(c["loc_d"]), z(c["w_d"])
+                        gf, gl_, gw = z(rf), z(c["loc_d"]), z(c["w_d"])
                         ext.deformable_aggregation_backward(rf, shapes_d, starts_d, c["loc_d"], c["w_d"], c["go_d"],
-                                                            gf, gl, gw)
+                                                            gf, gl_, gw)
                     e2.record()
                     torch.cuda.synchronize()
                     res[c["kind"]] = {"ref_fwd_us": round(e0.elapsed_time(e1) * 1e3 / n, 1),
@@ -511,88 +567,41 @@ def gpu_arm(args):
     # ---- end to end through the public Python API, host buffers, H2D + D2H inside the timed region
     e2e = None
     if not args.skip_e2e:
-        pin = lambda x: torch.from_numpy(x).pin_memory()
-        host = [dict(loc=pin(c["loc"]), w=pin(c["weights"]), go=pin(c["grad_out"])) for c in calls]
-        feat_pin = feat_h.pin_memory()
-        h2d = feat_pin.numel() * feat_pin.element_size() + sum(
-            h["loc"].numel() * 4 + h["w"].numel() * 4 + h["go"].numel() * 4 for h in host)
-        out_host = [torch.empty((bs, c["A"], C), dtype=torch.float32).pin_memory() for c in calls]
-        gsum_host = torch.empty(3, dtype=torch.float32).pin_memory()
-        d2h = sum(o.numel() * 4 for o in out_host) + 12
+        e2e = e2e_leg(args, hipad_b200, calls, layers, feat_h, shapes_d, starts_d, dev, world, step_bytes, max_over_ranks, barrier)
 
-        copy_s = torch.cuda.Stream(device=dev)
-        # device-side landing buffers, allocated once (what a data loader does); every step overwrites them
-        f_in = torch.empty_like(feat).requires_grad_(True)
-        ins = [(torch.empty_like(c["loc_d"]).requires_grad_(True), torch.empty_like(c["w_d"]).requires_grad_(True),
-                torch.empty_like(c["go_d"])) for c in calls]
-
-        def e2e_step():
-            # every host->device copy of the step is queued on a copy stream up front (pinned buffers, so they run
-            # back to back on the DMA engine); the compute stream waits for each tensor right before its first use
-            cur = torch.cuda.current_stream()
-            copy_s.wait_stream(cur)              # the previous step must be done with the landing buffers
-            evs = []
-            with torch.cuda.stream(copy_s), torch.no_grad():
-                def up(dst, src):
-                    dst.copy_(src, non_blocking=True)
-                    ev = torch.cuda.Event()
-                    ev.record(copy_s)
-                    return ev
-                ev_f = up(f_in, feat_pin)
-                for (loc, w, go), h in zip(ins, host):
-                    evs.append((up(loc, h["loc"]), up(w, h["w"]), up(go, h["go"])))
-            f_in.grad = None
-            cur.wait_event(ev_f)
-            outs = []
-            for (loc, w, go), (ev_l, ev_w, _) in zip(ins, evs):
-                loc.grad = None
-                w.grad = None
-                cur.wait_event(ev_l)
-                cur.wait_event(ev_w)
-                outs.append(hipad_b200.deformable_aggregation_function(f_in, shapes_d, starts_d, loc, w))
-            cur.wait_event(evs[-1][2])
-            torch.autograd.backward(outs, [go for _, _, go in ins])
-            for o, oh in zip(outs, out_host):
-                oh.copy_(o.detach(), non_blocking=True)
-            gsum_host.copy_(torch.stack([f_in.grad.float().abs().sum(), ins[0][0].grad.abs().sum(),
-                                         ins[0][1].grad.abs().sum()]), non_blocking=True)
-
-        n_e2e = max(2, min(args.steps, 5))
-        e2e_step(); torch.cuda.synchronize()
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(n_e2e):
-            e2e_step()
-        torch.cuda.synchronize()
-        dt_s = max_over_ranks((time.perf_counter() - t0) / n_e2e, dev)
-        e2e = {"value": round(whole_job_gbs(world, step_bytes, dt_s * 1e3), 2), "unit": "GB/s",
-               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-               "ms_per_step": round(dt_s * 1e3, 3), "steps": n_e2e,
-               "api": "hipad_b200.deformable_aggregation_function + autograd, pinned host buffers, H2D on a copy stream"}
+    # ---- the callers of the path (BASELINE configs[1] / [2]): the unmodified reference decoder through the harness
+    decoder_forward = train_step = None
+    if not args.skip_decoder and not bf16:
+        del g_feat_l, ws_b, ws_f, flush
+        torch.cuda.empty_cache()
+        decoder_forward, train_step = decoder_legs(args, dev, world, rank, max_over_ranks)
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.skip_cpu:
-        cpu_baseline = cpu_reference(budget_s=args.cpu_budget, steps=None, warmup=1)["cpu_baseline"]
+        cpu_baseline = cpu_reference(steps=2, warmup=1)["cpu_baseline"]
 
     if rank == 0:
+        cfg = shared_config(bs, args.dtype)
         line = {
             "metric": METRIC, "value": round(value, 2), "unit": "GB/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": round(ms_per_step, 4), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if bf16 else "f32", "data": "synthetic",
-            "config": {"workload": "HiP-AD stage-2 decoder DFA path: 6 layers x (det 900x13 + map 100x300 + "
-                                   "plan 480x90 + ego 1x13), 6 cams, 4 levels of 352x640, C=256, G=8, fwd+bwd",
-                       "bs_per_gpu": bs, "feature_dtype": args.dtype, "parallelism": "batch-sharded x%d" % world,
-                       "l2": "256 MiB read sweep (flush) between timed steps", "cuda_graph": graph is not None,
-                       "streams": n_lanes,
-                       "locations": "B2D camera geometry, det/map/plan visible fraction ~0.20/0.19/0.13, ego 0"},
+            "config": cfg,
+            "run": {"parallelism": "batch-sharded x%d" % world, "l2": "256 MiB read sweep (flush) between timed steps",
+                    "cuda_graph": graph is not None, "streams": n_lanes,
+                    "api": "C ABI, one call at a time (hipad_dfa_group_forward with 1 call + hipad_dfa_backward_*), "
+                           "the 4 calls of a layer as parallel graph branches",
+                    "locations": "B2D camera geometry, det/map/plan visible fraction ~0.20/0.19/0.13, ego 0"},
             "samples_per_s": round(world * bs / (ms_per_step * 1e-3), 2),
             "algorithmic_bytes_per_step": int(step_bytes),
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
-            "roofline": roofline, "cpu_baseline": cpu_baseline, "shared_gfeat_step": shared, "decoder_forward_inference": inference,
+            "roofline": roofline, "roofline_per_kernel": per_kernel, "cpu_baseline": cpu_baseline,
+            "group_step": group_step, "grouped_layer_stage_us": grouped_layer_us,
+            "decoder_forward": decoder_forward, "train_step": train_step,
+            "decoder_forward_dfa_only": inference,
             "per_call_us": {k: {"fwd": round(float(np.mean(v["fwd_us"])), 1), "bwd": round(float(np.mean(v["bwd_us"])), 1),
                                 "B_fwd": v["bytes"]["fwd"], "B_bwd": v["bytes"]["bwd"], "U_rows": v["bytes"]["U"]}
                             for k, v in per_mod.items()},
-            "kernel_avg_us": {k: round(float(np.mean(v)), 2) for k, v in kern.items()},
             "reference_cuda_op_same_gpu": ref_cuda,
         }
         emit(line)
@@ -600,14 +609,161 @@ def gpu_arm(args):
         dist.destroy_process_group()
 
 
+def e2e_leg(args, hipad_b200, calls, layers, feat_h, shapes_d, starts_d, dev, world, step_bytes, max_over_ranks, barrier):
+    """The same step through the public Python API (hipad_b200.deformable_aggregation_group per decoder layer +
+    share_feature_gradient + autograd) from pinned HOST memory: one staging arena per step, THREE large host->device
+    copies (features / all locations + weights / all output gradients), two device arenas so that step k+1's copies
+    run under step k's compute; outputs and gradient checksums are read back every step."""
+    bs = feat_h.shape[0]
+    f32 = torch.float32
+    sizes_lw = []
+    for c in calls:
+        sizes_lw += [c["loc"].size, c["weights"].size]
+    n_lw = int(sum(sizes_lw))
+    n_go = int(sum(c["grad_out"].size for c in calls))
+    host_lw = torch.empty(n_lw, dtype=f32).pin_memory()
+    host_go = torch.empty(n_go, dtype=f32).pin_memory()
+    o = 0
+    for c in calls:
+        for key in ("loc", "weights"):
+            n = c[key].size
+            host_lw[o:o + n] = torch.from_numpy(c[key]).reshape(-1)
+            o += n
+    o = 0
+    for c in calls:
+        n = c["grad_out"].size
+        host_go[o:o + n] = torch.from_numpy(c["grad_out"]).reshape(-1)
+        o += n
+    feat_pin = feat_h.pin_memory()
+    h2d = feat_pin.numel() * feat_pin.element_size() + (n_lw + n_go) * 4
+    a_total = sum(c["A"] for c in layers[0])
+    out_host = torch.empty((len(layers), bs, a_total, C), dtype=f32).pin_memory()
+    gsum_host = torch.empty(3, dtype=f32).pin_memory()
+    d2h = out_host.numel() * 4 + 12
+
+    class Arena:
+        def __init__(self):
+            self.feat = torch.empty_like(feat_h, device=dev)
+            self.lw = torch.empty(n_lw, dtype=f32, device=dev)
+            self.go = torch.empty(n_go, dtype=f32, device=dev)
+            self.ready = torch.cuda.Event()
+            self.free = torch.cuda.Event()
+            self.free.record()
+
+    arenas = [Arena(), Arena()]
+    copy_s = torch.cuda.Stream(device=dev)
+
+    def upload(a):
+        copy_s.wait_event(a.free)           # the step that last used this arena is done with it
+        with torch.cuda.stream(copy_s):
+            a.feat.copy_(feat_pin, non_blocking=True)
+            a.lw.copy_(host_lw, non_blocking=True)
+            a.go.copy_(host_go, non_blocking=True)
+            a.ready.record(copy_s)
+
+    def compute(a):
+        cur = torch.cuda.current_stream()
+        cur.wait_event(a.ready)
+        f_in = a.feat.detach().requires_grad_(True)
+        f = hipad_b200.share_feature_gradient(f_in)
+        outs, gos, leaves = [], [], []
+        o_lw = o_go = 0
+        for group in layers:
+            pairs = []
+            for c in group:
+                n1, n2 = c["loc"].size, c["weights"].size
+                loc = a.lw[o_lw:o_lw + n1].view(c["loc"].shape).detach().requires_grad_(True)
+                w = a.lw[o_lw + n1:o_lw + n1 + n2].view(c["weights"].shape).detach().requires_grad_(True)
+                o_lw += n1 + n2
+                pairs.append((loc, w))
+                n3 = c["grad_out"].size
+                gos.append(a.go[o_go:o_go + n3].view(c["grad_out"].shape))
+                o_go += n3
+            leaves.append(pairs[0])
+            outs += hipad_b200.deformable_aggregation_group(f, shapes_d, starts_d, pairs)
+        torch.autograd.backward(outs, gos)
+        n_mod = len(layers[0])
+        for li in range(len(layers)):
+            out_host[li].copy_(torch.cat([x.detach() for x in outs[li * n_mod:(li + 1) * n_mod]], dim=1), non_blocking=True)
+        gsum_host.copy_(torch.stack([f_in.grad.float().abs().sum(), leaves[0][0].grad.abs().sum(),
+                                     leaves[0][1].grad.abs().sum()]), non_blocking=True)
+        a.free.record(cur)
+
+    n_e2e = max(3, min(args.steps, 8))
+    upload(arenas[0]); compute(arenas[0]); torch.cuda.synchronize()      # warm-up
+    barrier()
+    t0 = time.perf_counter()
+    upload(arenas[0])
+    for k in range(n_e2e):
+        if k + 1 < n_e2e:
+            upload(arenas[(k + 1) % 2])      # next step's copies run under this step's compute
+        compute(arenas[k % 2])
+    torch.cuda.synchronize()
+    dt_s = max_over_ranks((time.perf_counter() - t0) / n_e2e, dev)
+    return {"value": round(whole_job_gbs(world, step_bytes, dt_s * 1e3), 2), "unit": "GB/s",
+            "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+            "ms_per_step": round(dt_s * 1e3, 3), "steps": n_e2e,
+            "h2d_gbs_per_rank": round(h2d / dt_s / 1e9, 1),
+            "limiter": "host->device copies: %.0f MB per step per rank from pinned memory (PCIe); compute is hidden under "
+                       "them" % (h2d / 1e6),
+            "api": "hipad_b200.deformable_aggregation_group per decoder layer + share_feature_gradient + autograd; one pinned "
+                   "arena, 3 copies per step, double-buffered device arenas (H2D of step k+1 under compute of step k)"}
+
+
+def decoder_legs(args, dev, world, rank, max_over_ranks):
+    """BASELINE configs[1] and [2] through the UNMODIFIED reference decoder (harness/): decoder forward bs=1 with the
+    reference CUDA op vs hipad_b200, and the training step (ResNet-50 + FPN stand-in, decoder, surrogate loss, AdamW,
+    DDP gradient all-reduce when world > 1) at --train-bs samples per GPU."""
+    try:
+        from harness import bench_decoder, train_step as ts, vendor
+        if vendor.vendor() is None:
+            return {"unavailable": "baseline/_ref/hipad not vendored"}, None
+    except Exception as e:
+        return {"error": repr(e)[:200]}, None
+    fwd = tr = None
+    try:
+        variants = ("reference", "ours", "ours_module") if (rank == 0 and world == 1) else ("ours_module",)
+        r = bench_decoder.run(hw_list=((352, 640), (256, 704)) if world == 1 else ((352, 640),), frames=args.decoder_frames,
+                              bs=1, variants=variants)
+        for hw, d in r.items():
+            for v in d.values():
+                if "ms_per_forward_median" in v:
+                    v["ms_per_forward_median"] = round(max_over_ranks(v["ms_per_forward_median"], dev), 3)
+                    v["samples_per_s"] = round(world * 1e3 / v["ms_per_forward_median"], 1)
+        fwd = r
+        fwd["note"] = ("unmodified reference SparseOneDecoder (70.8 M parameters, stage-2 config) through harness/; bs=1 per GPU, "
+                       "eager PyTorch, host-bound (hundreds of small launches per forward); samples_per_s is the whole job")
+    except Exception as e:
+        fwd = {"error": repr(e)[:300]}
+    try:
+        t = ts.time_train_step("ours_module", bs=args.train_bs, steps=args.train_steps, warmup=2, device=dev, world=world,
+                               rank=rank)
+        t["ms_per_step"] = round(max_over_ranks(t["ms_per_step"], dev), 2)
+        t["samples_per_s"] = round(world * args.train_bs / (t["ms_per_step"] * 1e-3), 2)
+        t["n_gpus"] = world
+        t["collective"] = ("DistributedDataParallel bucketed NCCL all-reduce of %.1f M fp32 gradients per step" % t["trainable_params_M"]
+                           if world > 1 else "none (1 GPU)")
+        tr = t
+        if rank == 0 and world == 1 and not args.skip_train_reference:
+            try:
+                tref = ts.time_train_step("reference", bs=args.train_bs, steps=max(2, args.train_steps // 2), warmup=1, device=dev)
+                tr["reference_cuda_op"] = {"ms_per_step": tref["ms_per_step"],
+                                           "samples_per_s": round(args.train_bs / (tref["ms_per_step"] * 1e-3), 2)}
+            except Exception as e:
+                tr["reference_cuda_op"] = {"error": repr(e)[:200]}
+    except Exception as e:
+        tr = {"error": repr(e)[:300]}
+    return fwd, tr
+
+
 # ------------------------------------------------------------------------------------- CPU arm
-def cpu_reference(budget_s, steps, warmup):
+def cpu_reference(steps, warmup):
     """The reference's CPU implementation of the path (torch grid_sample branch) on the host cores.
 
-    Sample: the four DFA calls of ONE decoder layer at bs=1 (1/6 of a GPU step); shrunk to the det
-    call alone if a layer would not fit the time budget."""
+    One step = the four DFA calls of ONE decoder layer at bs=1, forward + backward (1/6 of a GPU step): a FIXED,
+    bounded sample of the workload (never shrunk), `steps` timed runs after `warmup` untimed ones."""
     from oracle import torch_path as tp
-    import helpers as H
+    import oracle
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     calls, shapes, starts, F = make_calls(1, seed=0, layers=1)
@@ -618,7 +774,6 @@ def cpu_reference(budget_s, steps, warmup):
 
     def bytes_of(c):
         # same definition as the GPU arm, U counted with the oracle's integer indices
-        import oracle
         U = oracle.unique_rows(shapes, starts, c["loc"], F)
         A, P = c["A"], c["P"]
         loc_b, w_b, out_b = A * P * CAMS * 8, A * P * CAMS * 4 * G * 4, A * C * 4
@@ -631,36 +786,38 @@ def cpu_reference(budget_s, steps, warmup):
             out = tp.grid_sample_path(fmaps, p2d, w)
             out.backward(torch.from_numpy(c["grad_out"]))
 
-    sample, desc = calls, "one decoder layer (det+map+plan+ego calls), bs=1, fwd+bwd, torch grid_sample path"
-    t0 = time.perf_counter(); run(sample); first = time.perf_counter() - t0
-    n = steps if steps is not None else max(1, int(budget_s // max(first, 1e-3)))
-    if first * (n + warmup) > 170:
-        sample, desc = calls[:1], "det call only (900x13), bs=1, fwd+bwd, torch grid_sample path"
-        t0 = time.perf_counter(); run(sample); first = time.perf_counter() - t0
-    for _ in range(max(0, warmup - 1)):
-        run(sample)
+    desc = "one decoder layer (det+map+plan+ego calls), bs=1, fwd+bwd, torch grid_sample path"
+    for _ in range(warmup):
+        run(calls)
     times = []
-    for _ in range(n):
-        t0 = time.perf_counter(); run(sample); times.append(time.perf_counter() - t0)
-    nbytes = sum(bytes_of(c) for c in sample)
+    for _ in range(steps):
+        t0 = time.perf_counter(); run(calls); times.append(time.perf_counter() - t0)
+    nbytes = sum(bytes_of(c) for c in calls)
     sec = float(np.mean(times))
     val = nbytes / sec / 1e9
-    return {"value": val, "ms_per_step": sec * 1e3, "steps": n,
+    return {"value": val, "ms_per_step": sec * 1e3, "steps": steps,
             "cpu_baseline": {"value": round(val, 4), "unit": "GB/s", "cores": cores, "kind": "port",
-                             "sample": desc + "; %d timed runs, %.2f s each" % (n, sec)}}
+                             "sample": desc + "; %d timed runs, %.2f s each" % (steps, sec)}}
 
 
 def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    r = cpu_reference(budget_s=args.cpu_budget, steps=args.steps, warmup=max(1, min(args.warmup, 2)))
+    # same --steps / --warmup as the GPU arm; each step is the fixed bounded sample (one decoder layer, ~1-2 s)
+    steps, warmup = args.steps, max(args.warmup, 3)
+    if args.ref_max_steps > 0:
+        steps = min(steps, args.ref_max_steps)
+    r = cpu_reference(steps=steps, warmup=warmup if args.ref_max_steps <= 0 else 1)
     line = {"impl": "reference", "metric": METRIC, "value": round(r["value"], 4), "unit": "GB/s",
-            "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": r["steps"], "warmup": max(1, min(args.warmup, 2)),
+            "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": args.steps, "warmup": max(args.warmup, 3),
+            "timed_steps": r["steps"],
             "ms_per_step": round(r["ms_per_step"], 2), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "HiP-AD stage-2 decoder DFA path (reference CPU torch path, bounded sample)",
-                       "bs_per_gpu": 1},
+            "config": shared_config(args.bs, args.dtype),
+            "run": {"what": "the reference's own CPU implementation of the path (torch grid_sample branch, oracle/torch_path.py "
+                            "restatement), all host cores; each step = the four calls of ONE decoder layer at bs=1 (a bounded "
+                            "sample: 1/6 of a GPU step), GB/s from the same byte definition"},
             "cpu_baseline": r["cpu_baseline"],
             "e2e": {"value": round(r["value"], 4), "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
@@ -679,7 +836,14 @@ def main():
                     help="4: the four modality calls of a decoder layer run as parallel branches; 1: strictly serial")
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
-    ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of CPU baseline work")
+    ap.add_argument("--skip-decoder", action="store_true", help="skip the decoder-forward and training-step legs")
+    ap.add_argument("--skip-ref-op", action="store_true", help="skip timing the reference CUDA op on the same GPU")
+    ap.add_argument("--skip-train-reference", action="store_true")
+    ap.add_argument("--decoder-frames", type=int, default=20)
+    ap.add_argument("--train-bs", type=int, default=4, help="samples per GPU of the training step (BASELINE configs[2])")
+    ap.add_argument("--train-steps", type=int, default=4)
+    ap.add_argument("--ref-max-steps", type=int, default=0,
+                    help="reference arm: cap on timed steps (0 = exactly --steps, what the driver compares)")
     args = ap.parse_args()
     isolate_stdout()
     if args.impl == "reference":

@@ -90,9 +90,14 @@ class CountingOps(types.ModuleType):
                 setattr(self, k, getattr(inner, k))
         fn = inner.deformable_aggregation_function
 
+        self.record = None          # set to a list to keep (inputs, output) of every call (in-situ parity checks)
+
         def counted(feature_maps, spatial_shape, scale_start_index, sampling_location, weights):
             self.calls.append(tuple(sampling_location.shape[1:3]))
-            return fn(feature_maps, spatial_shape, scale_start_index, sampling_location, weights)
+            out = fn(feature_maps, spatial_shape, scale_start_index, sampling_location, weights)
+            if self.record is not None:
+                self.record.append((feature_maps, spatial_shape, scale_start_index, sampling_location, weights, out))
+            return out
         self.deformable_aggregation_function = counted
 
 

@@ -4,9 +4,11 @@ baseline/_ref/hipad, never committed) runs with ``sys.modules['projects.mmdet3d_
 CPU part (no GPU): the harness builds the 70.8 M-parameter stage-2 decoder through the mmcv stand-in and runs two
 consecutive frames with the C oracle standing in for the op: exactly 24 aggregation calls per forward, in the order
 det -> map -> plan -> ego, with the stage-2 shapes.
-GPU part: the same decoder three times with identical weights — the reference's own ops package over its own CUDA
-extension (oracle/_ref), ``hipad_b200.ops``, and ``hipad_b200.ops`` + ``hipad_b200.DeformableFeatureAggregation`` —
-every returned tensor compared over three frames.
+GPU part: (i) every one of the 24 aggregation calls per frame of the reference decoder (running on its own CUDA op)
+is replayed through ``hipad_b200`` on the same inputs, per call and grouped per layer: outputs within 1e-5; (ii) the
+same decoder three times with identical weights — the reference's own ops package over its own CUDA extension
+(oracle/_ref), ``hipad_b200.ops``, and ``hipad_b200.ops`` + ``hipad_b200.DeformableFeatureAggregation`` — whole-decoder
+outputs compared within the reference's own run-to-run noise (its atomics make it non-deterministic).
 """
 import os
 import sys
@@ -78,11 +80,48 @@ def _max_rel(a, b):
 @pytest.mark.gpu
 @needs_vendored
 @pytest.mark.parametrize("hw", [(352, 640), (256, 704)])
-def test_decoder_outputs_match_reference_cuda_op(cuda_lib, hw):
+def test_every_aggregation_call_of_the_decoder_matches_in_situ(cuda_lib, hw):
+    """The reference decoder runs three consecutive frames on the reference's OWN CUDA op; the inputs of each of its
+    24 aggregation calls per frame (model-generated key points, softmaxed weights, temporal caches populated) are then
+    fed to hipad_b200's op: every output within 1e-5 of the reference op's.  This is the decoder-level parity that does
+    not depend on how the rest of the network amplifies last-bit differences."""
+    from oracle import build_ref
+    import hipad_b200
+    if not build_ref.available():
+        pytest.skip("oracle/_ref not built")
+    ref = HD.build_decoder("reference", hw=hw, device="cuda")
+    HD.use_sdpa_attention(ref)
+    frames = HD.make_frames(3, bs=1, hw=hw, device="cuda")
+    worst = 0.0
+    with torch.no_grad():
+        for levels, metas in frames:
+            ref._hipad_ops.record = []
+            HD.run_frame(ref, levels, metas)
+            rec, ref._hipad_ops.record = ref._hipad_ops.record, None
+            assert [tuple(r[3].shape[1:3]) for r in rec] == STAGE2_CALLS
+            for feat, shapes, starts, loc, w, out_ref in rec:
+                out = hipad_b200.deformable_aggregation_function(feat, shapes, starts, loc, w)
+                worst = max(worst, _max_rel(out, out_ref))
+            # the four calls of each layer as ONE grouped launch: same outputs
+            for layer in range(6):
+                grp = rec[4 * layer:4 * layer + 4]
+                outs = hipad_b200.deformable_aggregation_group(grp[0][0], grp[0][1], grp[0][2], [(r[3], r[4]) for r in grp])
+                for o, r in zip(outs, grp):
+                    worst = max(worst, _max_rel(o, r[5]))
+    assert worst <= 1e-5, worst
+
+
+@pytest.mark.gpu
+@needs_vendored
+def test_decoder_outputs_match_reference_cuda_op_within_its_own_noise(cuda_lib):
+    """Whole-decoder outputs, three variants with identical weights.  The reference op accumulates with fp32 atomics,
+    so the reference decoder does not reproduce ITSELF run to run (measured: ~1e-3 on the first frame; from the second
+    frame on the temporal top-k caches amplify it to O(1) in a few rows).  Ours is bitwise reproducible, and on the
+    first frame it is as close to the reference as the reference is to itself."""
     from oracle import build_ref
     if not build_ref.available():
         pytest.skip("oracle/_ref not built")
-    dev = "cuda"
+    hw, dev = (352, 640), "cuda"
     ref = HD.build_decoder("reference", hw=hw, device=dev)
     variants = {"ours": HD.build_decoder("ours", hw=hw, device=dev),
                 "ours_module": HD.build_decoder("ours_module", hw=hw, device=dev)}
@@ -90,30 +129,40 @@ def test_decoder_outputs_match_reference_cuda_op(cuda_lib, hw):
         HD.copy_weights(d, ref)
     for d in [ref] + list(variants.values()):     # fp32 attention: flash-attn's fp16 would sit between the variants
         HD.use_sdpa_attention(d)
-    frames = HD.make_frames(3, bs=1, hw=hw, device=dev)
-    outs = {}
-    with torch.no_grad():
-        for name, d in dict(reference=ref, **variants).items():
-            HD.reset(d)
-            outs[name] = []
+    frames = HD.make_frames(2, bs=1, hw=hw, device=dev)
+
+    def run(d, count_calls):
+        HD.reset(d)
+        outs = []
+        with torch.no_grad():
             for levels, metas in frames:
                 n0 = len(d._hipad_ops.calls)
-                outs[name].append(HD.flatten_outputs(HD.run_frame(d, levels, metas)))
-                if name != "ours_module":        # the module variant calls the fused entry point, not the 5-arg op
+                outs.append({k: v.detach().clone() for k, v in HD.flatten_outputs(HD.run_frame(d, levels, metas)).items()})
+                if count_calls:
                     assert d._hipad_ops.calls[n0:] == STAGE2_CALLS
-    torch.cuda.synchronize()
-    worst = {}
-    for name in variants:
-        for f, (a, b) in enumerate(zip(outs[name], outs["reference"])):
-            assert a.keys() == b.keys()
-            for k in a:
-                assert a[k].shape == b[k].shape, (name, f, k)
-                if a[k].dtype.is_floating_point:
-                    worst[(name, f, k)] = _max_rel(a[k], b[k])
-                else:
-                    worst[(name, f, k)] = 0.0 if torch.equal(a[k], b[k]) else 1.0
-    bad = {k: v for k, v in worst.items() if not v <= DECODER_TOL}
-    assert not bad, sorted(bad.items(), key=lambda kv: -kv[1])[:10]
+        torch.cuda.synchronize()
+        return outs
+
+    def worst(a, b):
+        w = 0.0
+        for k in b:
+            assert a[k].shape == b[k].shape, k
+            if a[k].dtype.is_floating_point:
+                w = max(w, _max_rel(a[k], b[k]))
+        return w
+
+    r1, r2 = run(ref, True), run(ref, True)
+    noise = worst(r2[0], r1[0])                               # reference vs itself, first frame
+    for name, d in variants.items():
+        o1 = run(d, name == "ours")
+        o2 = run(d, False)
+        for fa, fb in zip(o1, o2):                            # ours: bitwise reproducible, every frame
+            for k in fa:
+                assert torch.equal(fa[k], fb[k]), (name, k)
+        assert worst(o1[0], r1[0]) <= max(DECODER_TOL, 3.0 * noise), (name, worst(o1[0], r1[0]), noise)
+        for f in o1:
+            for k, v in f.items():
+                assert torch.isfinite(v.float()).all(), (name, k)
 
 
 @pytest.mark.gpu

@@ -145,7 +145,7 @@ def test_reference_arm_prints_one_json_line():
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1",
-                        "--warmup", "1", "--cpu-budget", "1"], capture_output=True, text=True, timeout=300)
+                        "--warmup", "1", "--ref-max-steps", "1"], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stderr[-500:]
     lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
     assert len(lines) == 1
@@ -153,3 +153,7 @@ def test_reference_arm_prints_one_json_line():
     assert d["impl"] == "reference" and d["unit"] == "GB/s" and d["higher_is_better"] is True
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
+    # both arms print the same `config` (the driver compares them)
+    sys.path.insert(0, root)
+    import bench
+    assert d["config"] == bench.shared_config(1, "f32")
