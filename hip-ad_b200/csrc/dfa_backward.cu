@@ -188,6 +188,8 @@ int launch_group_backward(const GroupBwdArgs& a) {
         if (!c.loc || !c.weights || !c.g_loc || !c.g_w || c.A <= 0 || c.P <= 0) return -1;
         // float2 / float4 accesses of the kernels (reject instead of faulting on odd sub-buffers)
         if (reinterpret_cast<uintptr_t>(c.loc) % 8 != 0 || reinterpret_cast<uintptr_t>(c.g_loc) % 8 != 0) return -1;
+        // the kernels zero / write weight-gradient rows with 16-byte stores when a row (L*G floats) allows it
+        if ((d.L * d.G) % 4 == 0 && reinterpret_cast<uintptr_t>(c.g_w) % 16 != 0) return -1;
         al = al && (reinterpret_cast<uintptr_t>(c.g_w) % 16 == 0) && (reinterpret_cast<uintptr_t>(c.weights) % 16 == 0);
         if ((long long)c.A * c.P > (long long)kMaxChunks * kVisChunk) return -2;
         if ((long long)c.A * c.P * d.cams * d.L * d.G >= (1LL << 30)) return -2;

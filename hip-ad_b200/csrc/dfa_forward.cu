@@ -51,6 +51,8 @@ int launch_forward(const FwdArgs& a) {
                     (reinterpret_cast<uintptr_t>(a.out) % 16 == 0);
     const KernelShape ks = pick_shape(a.type, d.C, d.G, al);
     if (!ks.ok || d.cams * d.L > kMaxCamLevels || (long long)d.num_feat * d.C >= (1LL << 30)) return -2;
+    // float2 accesses of the kernels: reject odd sub-buffers instead of faulting
+    if (reinterpret_cast<uintptr_t>(a.loc) % 8 != 0 || reinterpret_cast<uintptr_t>(a.loc_out) % 8 != 0) return -1;
     const int mode = a.fused ? kFused : kFwd;
     if (a.fused && (256 % d.G != 0)) return -2;
     if (!a.fused && al && d.P * d.cams <= 96 && group_kernel_supported(a.type, d.C, d.L, d.G, d.cams)) {

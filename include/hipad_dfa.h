@@ -25,7 +25,8 @@
  *
  * Alignment: mc_ms_feat, output, grad_output, grad_mc_ms_feat, weights and grad_weights should be 16-byte aligned
  * (the 16-byte vector kernels are used then; otherwise a scalar kernel family is); sample_location,
- * grad_sampling_location and sample_location_out MUST be 8-byte aligned (HIPAD_DFA_ERR_BAD_ARGUMENT otherwise).
+ * grad_sampling_location and sample_location_out MUST be 8-byte aligned, and grad_weights MUST be 16-byte aligned
+ * when num_scale*num_groups is a multiple of 4 (HIPAD_DFA_ERR_BAD_ARGUMENT otherwise).
  *
  * Tensor layouts (row-major, identical to the reference, deformable_aggregation.cpp:22-28):
  *   mc_ms_feat        [bs, num_feat, num_embeds]               f32 or bf16

@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """One stage-2 decoder layer (det 900x13 + map 100x300 + plan 480x90 + ego 1x13, 352x640, C=256, G=8): CUDA-event
 times of the forward / backward per call and grouped, L2 flushed before every timed launch sequence.
-usage: python profiles/run_group.py [bs] [f32|bf16]   (env knobs of the kernels apply: HIPAD_DFA_GROUP_WARPS, ...)"""
+usage: python profiles/run_group.py [bs] [f32|bf16] [HxW] [plan anchors]   (env knobs of the kernels apply)
+       HxW = 352x640 (stage-2, default) | 256x704 (BASELINE configs[0] geometry) | 512x1408 (configs[4], with 48 plan anchors)"""
 import ctypes
 import json
 import os
@@ -20,7 +21,9 @@ bs = int(sys.argv[1]) if len(sys.argv) > 1 else 1
 bf16 = len(sys.argv) > 2 and sys.argv[2] == "bf16"
 lib = _lib.get()
 dev = torch.device("cuda")
-LV = H.LEVELS_352x640
+HW = tuple(int(x) for x in sys.argv[3].split("x")) if len(sys.argv) > 3 else (352, 640)
+PLAN_A = int(sys.argv[4]) if len(sys.argv) > 4 else 480
+LV = [(HW[0] // s_, HW[1] // s_) for s_ in (4, 8, 16, 32)]
 shapes, starts, F = H.level_tables(LV, 6)
 C, G, L, CAMS = 256, 8, 4, 6
 rng = np.random.default_rng(0)
@@ -28,10 +31,10 @@ feat = torch.from_numpy(rng.standard_normal((bs, F, C), dtype=np.float32)).to(de
 if bf16:
     feat = feat.bfloat16()
 sh, st = torch.from_numpy(shapes).to(dev), torch.from_numpy(starts).to(dev)
-MODS = (("det", 900, 13), ("map", 100, 300), ("plan", 480, 90), ("ego", 1, 13))
+MODS = (("det", 900, 13), ("map", 100, 300), ("plan", PLAN_A, 90), ("ego", 1, 13))
 calls = []
 for i, (kind, A, P) in enumerate(MODS):
-    c = H.make_geo_case(10 + i, "det" if kind == "ego" else kind, bs, LV, (352, 640), A=A, P=P, with_feat=False)
+    c = H.make_geo_case(10 + i, "det" if kind == "ego" else kind, bs, LV, HW, A=A, P=P, with_feat=False)
     loc = c["loc"] if kind != "ego" else np.full_like(c["loc"], -0.5)
     d = dict(kind=kind, A=A, P=P, loc=torch.from_numpy(loc).to(dev), w=torch.from_numpy(c["weights"]).to(dev),
              go=torch.from_numpy(rng.standard_normal((bs, A, C), dtype=np.float32)).to(dev))
@@ -94,7 +97,7 @@ def timed(fn, reps=7):
     return round(float(np.median(ts[2:])), 1)
 
 
-res = {"bs": bs, "dtype": "bf16" if bf16 else "f32", "env": {k: v for k, v in os.environ.items() if k.startswith("HIPAD_")}}
+res = {"bs": bs, "dtype": "bf16" if bf16 else "f32", "input_hw": list(HW), "plan_anchors": PLAN_A, "feature_MB": round(feat.numel() * feat.element_size() / 1e6, 1), "env": {k: v for k, v in os.environ.items() if k.startswith("HIPAD_")}}
 wf = {c["kind"]: ws_fwd([c]) for c in calls}
 wb = {c["kind"]: ws_bwd([c]) for c in calls}
 wf_all, wb_all = ws_fwd(calls), ws_bwd(calls)

@@ -32,13 +32,16 @@ for A in (900, 1800, 2700, 3600):
             dims = (bs, 6, F, 256, 4, A, P, 8)
             nb = lib.hipad_dfa_backward_workspace_bytes(*dims); ws = torch.empty(nb, dtype=torch.uint8, device=dev)
             s = torch.cuda.current_stream().cuda_stream
-            fwd = lib.hipad_dfa_forward_bf16 if dt == "bf16" else lib.hipad_dfa_forward_f32
+            import ctypes
+            tab = _lib.call_table([(loc.data_ptr(), w.data_ptr(), None, None, A, P)]); tp = ctypes.cast(tab, ctypes.c_void_p)
+            wf = torch.empty(max(256, lib.hipad_dfa_group_forward_workspace_bytes(tp, 1, bs, 6, 256)), dtype=torch.uint8, device=dev)
             tf, tb = [], []
             for rep in range(6):
                 flush.sum()
                 e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
                 e[0].record()
-                _lib.check(fwd(out.data_ptr(), feat.data_ptr(), sh.data_ptr(), st.data_ptr(), loc.data_ptr(), w.data_ptr(), *dims, s), "fwd")
+                _lib.check(lib.hipad_dfa_group_forward(int(dt == "bf16"), out.data_ptr(), feat.data_ptr(), sh.data_ptr(), st.data_ptr(), tp, 1,
+                                                       bs, 6, F, 256, 4, 8, wf.data_ptr(), wf.numel(), s), "fwd")
                 e[1].record()
                 _lib.check(lib.hipad_dfa_backward_stages(int(dt == "bf16"), 7, feat.data_ptr(), sh.data_ptr(), st.data_ptr(), loc.data_ptr(),
                                                          w.data_ptr(), go.data_ptr(), g_feat.data_ptr(), g_loc.data_ptr(), g_w.data_ptr(),

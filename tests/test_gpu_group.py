@@ -286,3 +286,36 @@ def test_reference_op_cells_at_near_integer_coordinates(ops):
     torch.cuda.synchronize()
     assert rel_err(out.detach().cpu().numpy(), ref_out.cpu().numpy()) <= FP32_TOL
     assert rel_err(fl.grad.cpu().numpy(), r_loc.cpu().numpy()) <= FP32_TOL
+
+
+def test_misaligned_sub_buffers_are_rejected_not_faulted(ops, cuda_lib):
+    """a g_w / location pointer that is only 4-byte aligned (a sub-buffer) must give a clean status."""
+    case = H.make_case(40, 1, 6, SMALL_LV, 256, 8, 12, 5)
+    feat, go = dev(case["feat"]), dev(case["grad_out"])
+    sh, st = dev(case["shapes"]).int(), dev(case["starts"]).int()
+    bs, F, C = feat.shape
+    dims = (bs, 6, F, C, 4, 12, 5, 8)
+    loc_buf = torch.zeros(case["loc"].size + 1, device="cuda"); loc_buf[1:] = dev(case["loc"]).reshape(-1)
+    w_buf = torch.zeros(case["weights"].size + 1, device="cuda"); w_buf[1:] = dev(case["weights"]).reshape(-1)
+    loc_ok, w_ok = dev(case["loc"]), dev(case["weights"])
+    g_loc, g_w = torch.empty_like(loc_ok), torch.empty(w_ok.numel() + 1, device="cuda")
+    g_feat = torch.empty_like(feat)
+    nb = cuda_lib.hipad_dfa_backward_workspace_bytes(*dims)
+    ws = torch.empty(nb, dtype=torch.uint8, device="cuda")
+    s = torch.cuda.current_stream().cuda_stream
+    out = torch.empty((bs, 12, C), device="cuda")
+    # forward with a location pointer that is 4 bytes off an 8-byte boundary
+    assert cuda_lib.hipad_dfa_forward_f32(out.data_ptr(), feat.data_ptr(), sh.data_ptr(), st.data_ptr(),
+                                          loc_buf.data_ptr() + 4, w_ok.data_ptr(), *dims, s) == -1
+    # backward with a weight-gradient pointer that is 4 bytes off a 16-byte boundary
+    assert cuda_lib.hipad_dfa_backward_f32(feat.data_ptr(), sh.data_ptr(), st.data_ptr(), loc_ok.data_ptr(), w_ok.data_ptr(),
+                                           go.data_ptr(), g_feat.data_ptr(), g_loc.data_ptr(), g_w.data_ptr() + 4, *dims,
+                                           ws.data_ptr(), nb, s) == -1
+    # weights that are only 4-byte aligned are legal: the scalar kernel family takes them
+    out2 = torch.empty_like(out)
+    assert cuda_lib.hipad_dfa_forward_f32(out2.data_ptr(), feat.data_ptr(), sh.data_ptr(), st.data_ptr(),
+                                          loc_ok.data_ptr(), w_buf.data_ptr() + 4, *dims, s) == 0
+    assert cuda_lib.hipad_dfa_forward_f32(out.data_ptr(), feat.data_ptr(), sh.data_ptr(), st.data_ptr(),
+                                          loc_ok.data_ptr(), w_ok.data_ptr(), *dims, s) == 0
+    torch.cuda.synchronize()
+    assert rel_err(out2.cpu().numpy(), out.cpu().numpy()) <= FP32_TOL
