@@ -17,6 +17,7 @@ from .ops import (  # noqa: F401
 )
 from .blocks import (  # noqa: F401
     DeformableFeatureAggregation,
+    aggregate_layer,
     SparseBox3DKeyPointsGenerator,
     SparsePoint3DKeyPointsGenerator,
 )

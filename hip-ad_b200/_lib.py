@@ -34,6 +34,8 @@ _SIGNATURES = {
     "hipad_dfa_group_backward": ([_i, _i, _p, _p, _p, _p, _i, _p, _p] + [_i] * 6 + [_p, ctypes.c_size_t, _p], _i),
     "hipad_dfa_group_backward_stages": ([_i, _i, _i, _p, _p, _p, _p, _i, _p, _p] + [_i] * 6 + [_p, ctypes.c_size_t, _p], _i),
     "hipad_dfa_debug_counters_offset": (_DIMS8, ctypes.c_size_t),
+    "hipad_dfa_weights_forward": ([_p, _p, _p, _p, ctypes.c_ulonglong, ctypes.c_float, ctypes.c_longlong, _i, _i, _i, _i, _p], _i),
+    "hipad_dfa_weights_backward": ([_p, _p, _p, _p, _p, ctypes.c_ulonglong, ctypes.c_float, ctypes.c_longlong, _i, _i, _i, _i, _p], _i),
 }
 
 

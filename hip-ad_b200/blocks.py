@@ -10,8 +10,9 @@ module is usable without mmcv.  When mmcv *is* importable the classes are also r
 Compute paths of ``forward`` (selected by the same ``use_deformable_func`` flag as the reference):
   use_deformable_func=True, inference (no grad)  -> ONE fused CUDA launch: projection + group
         softmax + aggregation (``ops.fused_deformable_aggregation``)
-  use_deformable_func=True, training             -> reference op chain with our CUDA op
-        (``ops.deformable_aggregation_function``), gradients from the deterministic backward
+  use_deformable_func=True, training             -> logits -> ``ops.aggregation_weights`` (softmax + attn-drop mask +
+        permute in one kernel each way) -> ``ops.deformable_aggregation_function``, gradients from the
+        deterministic backward
   use_deformable_func=False                      -> the reference's own pure-torch grid_sample
         branch, kept because it is part of the module's documented interface.  It is an explicit
         opt-in, never selected automatically, and is NOT a fallback for a missing CUDA library.
@@ -266,14 +267,12 @@ class DeformableFeatureAggregation(nn.Module):
                 features = _ops.fused_deformable_aggregation(
                     feature_maps, key_points, metas["projection_mat"], metas.get("image_wh"), logits)
             else:
-                weights = self._get_weights(instance_feature, anchor_embed, metas)
                 points_2d = (
                     self.project_points(key_points, metas["projection_mat"], metas.get("image_wh"))
                     .permute(0, 2, 3, 1, 4)
                     .reshape(bs, num_anchor, self.num_pts, self.num_cams, 2)
                 )
-                weights = weights.permute(0, 1, 4, 2, 3, 5).contiguous().reshape(
-                    bs, num_anchor, self.num_pts, self.num_cams, self.num_levels, self.num_groups)
+                weights = self._get_op_weights(instance_feature, anchor_embed, metas)
                 features = _ops.deformable_aggregation_function(*feature_maps, points_2d, weights)
             features = features.reshape(bs, num_anchor, self.embed_dims)
         else:
@@ -308,6 +307,18 @@ class DeformableFeatureAggregation(nn.Module):
                 cam = self.camera_encoder(metas["projection_mat"][:, :, :3].reshape(bs, self.num_cams, -1))
                 feature = feature[:, :, None] + cam[:, None]
         return self.weights_fc(feature)
+
+    def _get_op_weights(self, instance_feature, anchor_embed, metas=None):
+        """Aggregation weights in the op's layout [bs, A, P, cams, L, G].  On CUDA: one kernel each way for softmax +
+        attn-drop mask + permute (``ops.aggregation_weights``); otherwise the reference's chain of torch ops."""
+        bs, num_anchor = instance_feature.shape[:2]
+        logits = self._get_logits(instance_feature, anchor_embed, metas)
+        if logits.is_cuda and 256 % self.num_groups == 0:
+            drop = self.attn_drop if (self.training and self.attn_drop > 0) else 0.0
+            return _ops.aggregation_weights(logits, self.num_cams, self.num_levels, self.num_pts, self.num_groups, drop)
+        weights = self._get_weights(instance_feature, anchor_embed, metas)
+        return weights.permute(0, 1, 4, 2, 3, 5).contiguous().reshape(
+            bs, num_anchor, self.num_pts, self.num_cams, self.num_levels, self.num_groups)
 
     def _get_weights(self, instance_feature, anchor_embed, metas=None):
         """Softmax over cams*levels*points per group -> [bs, A, cams, L, P, G] (blocks.py:178-214)."""
@@ -355,6 +366,36 @@ class DeformableFeatureAggregation(nn.Module):
         grouped = features.reshape(features.shape[:-1] + (self.num_groups, self.group_dims))
         fused = (weights[..., None] * grouped).sum(dim=2).sum(dim=2)
         return fused.reshape(bs, num_anchor, self.num_pts, self.embed_dims)
+
+
+def aggregate_layer(calls, feature_maps, metas):
+    """The aggregation modules of ONE decoder layer (the reference's ``"deformable"`` branch,
+    ``sparse_onedecoder.py:867-887``, calls them one after the other) through ONE grouped launch.
+
+    calls: list of ``(module, instance_feature, anchor, anchor_embed)`` — ``DeformableFeatureAggregation`` instances
+    that read the same ``feature_maps``.  Returns the list of module outputs, identical to calling each module's
+    ``forward`` (same key points, weights, projected locations, ``output_proj`` + residual); the four aggregations
+    share one forward launch, one backward chain and one feature gradient
+    (``ops.deformable_aggregation_group``)."""
+    pairs = []
+    for m, inst, anchor, embed in calls:
+        if not m.use_deformable_func:
+            raise ValueError("aggregate_layer needs use_deformable_func=True modules")
+        bs, num_anchor = inst.shape[:2]
+        key_points = m.kps_generator(anchor, embed, inst)
+        points_2d = (m.project_points(key_points, metas["projection_mat"], metas.get("image_wh"))
+                     .permute(0, 2, 3, 1, 4).reshape(bs, num_anchor, m.num_pts, m.num_cams, 2))
+        pairs.append((points_2d, m._get_op_weights(inst, embed, metas)))
+    feats = _ops.deformable_aggregation_group(feature_maps[0], feature_maps[1], feature_maps[2], pairs)
+    outs = []
+    for (m, inst, _, _), f in zip(calls, feats):
+        out = m.proj_drop(m.output_proj(f.reshape(inst.shape[0], inst.shape[1], m.embed_dims)))
+        if m.residual_mode == "add":
+            out = out + inst
+        elif m.residual_mode == "cat":
+            out = torch.cat([out, inst], dim=-1)
+        outs.append(out)
+    return outs
 
 
 def _register_with_mmcv():

@@ -12,7 +12,7 @@ CSRC = os.path.join(_HERE, "csrc")
 LIB_DIR = os.path.join(_HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libhipad_dfa.so")
 OBJ_DIR = os.path.join(LIB_DIR, "obj")
-SOURCES = ["dfa_forward.cu", "dfa_backward.cu", "dfa_group.cu", "dfa_api.cu", "dfa_format.cu"]
+SOURCES = ["dfa_forward.cu", "dfa_backward.cu", "dfa_group.cu", "dfa_api.cu", "dfa_format.cu", "dfa_weights.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC"]
 

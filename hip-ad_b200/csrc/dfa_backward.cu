@@ -361,11 +361,21 @@ int launch_group_backward(const GroupBwdArgs& a) {
                                  chain>>>(gp);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return finish((int)e);
-        const size_t sort_smem = band_sort_smem_bytes(wl.n_chunks);
-        e = ensure_smem(dfa_band_sort_kernel, sort_smem);
-        if (e != cudaSuccess) return finish((int)e);
-        dfa_band_sort_kernel<<<dim3((unsigned)gp.NB, (unsigned)(d.cams * d.L), (unsigned)d.bs), kSortThreads, sort_smem,
-                               chain>>>(gp);
+        // 512-thread sort CTAs; HIPAD_DFA_SORT_THREADS=256 selects 256-thread CTAs with half the shared memory
+        // (measured slower on the stage-2 layer, 116 vs 93 us: the band CTA's cost is the walk over its camera's list)
+        const bool wide = hipad_env_int("HIPAD_DFA_SORT_THREADS", 512) >= 512;
+        const dim3 sgrid((unsigned)gp.NB, (unsigned)(d.cams * d.L), (unsigned)d.bs);
+        if (wide) {
+            const size_t sort_smem = band_sort_smem_bytes(wl.n_chunks, 512, 8192);
+            e = ensure_smem(dfa_band_sort_kernel<512, 8192>, sort_smem);
+            if (e != cudaSuccess) return finish((int)e);
+            dfa_band_sort_kernel<512, 8192><<<sgrid, 512, sort_smem, chain>>>(gp);
+        } else {
+            const size_t sort_smem = band_sort_smem_bytes(wl.n_chunks, 256, 4096);
+            e = ensure_smem(dfa_band_sort_kernel<256, 4096>, sort_smem);
+            if (e != cudaSuccess) return finish((int)e);
+            dfa_band_sort_kernel<256, 4096><<<sgrid, 256, sort_smem, chain>>>(gp);
+        }
         e = cudaGetLastError();
         if (e != cudaSuccess) return finish((int)e);
         if (int e2 = debug_sync("compaction / band sort", chain)) return finish(e2);

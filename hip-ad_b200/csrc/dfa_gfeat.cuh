@@ -33,11 +33,8 @@ namespace hipad {
 
 constexpr int kVisChunk = 1024;          // samples per compaction chunk
 constexpr int kVisThreads = 256;
-constexpr int kSortThreads = 512;
-constexpr int kSortWarps = kSortThreads / 32;
 constexpr int kRadixBits = 8;
 constexpr int kRadix = 1 << kRadixBits;
-constexpr int kBandCap = 8192;           // packed words per ping-pong half kept in shared memory
 constexpr int kMaxBands = 32;
 constexpr int kScanUnroll = 8;           // independent loads in flight per lane in the band kernel's scans
 constexpr int kSegScale = 8;             // ints of segment table per feature row (upper bound, see seg_offset)
@@ -215,9 +212,10 @@ __global__ void __launch_bounds__(kVisThreads) dfa_vis_compact_kernel(const Gfea
 // ------------------------------------------------------------------------------------------ band sort
 // Stable LSD radix sort of n packed words on bits [lo_bit, lo_bit + nbits) by one CTA of kSortThreads.
 // a/b: ping-pong arrays (shared or global).  Returns the array holding the result.
-template <typename W>
+template <typename W, int kT>
 __device__ W* block_radix_sort(W* a, W* b, int n, int lo_bit, int nbits, unsigned* hist /*[kSortWarps][kRadix]*/,
                                unsigned* tot /*[kRadix + 32]*/) {
+    constexpr int kSortWarps = kT / 32;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     int chunk = (n + kSortWarps - 1) / kSortWarps;
     chunk = (chunk + 31) & ~31;
@@ -294,9 +292,10 @@ struct BandCtx {
 };
 
 // compaction (chunk order, then order inside the chunk) + sort + record/segment emission of one band
-template <typename W>
+template <typename W, int kT>
 __device__ void band_sort_body(const GfeatParams& p, const BandCtx& bc, W* a, W* b, unsigned* hist, unsigned* tot,
                                int* seg_band) {
+    constexpr int kSortThreads = kT, kSortWarps = kT / 32;
     const Dims d = p.d;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int AP = p.n_ids;
@@ -324,12 +323,14 @@ __device__ void band_sort_body(const GfeatParams& p, const BandCtx& bc, W* a, W*
 #pragma unroll
             for (int u = 0; u < kScanUnroll; ++u) {
                 if (i0 + u * 32 >= cnt) break;   // warp-uniform
-                const Quad q = quad_setup(xy[u].x, xy[u].y, bc.h, bc.w);
-                const int qr = q.h_low + 1;
+                // every band CTA of the bucket walks the camera's whole list: test the band with the row index alone
+                // (the same FMA + floor as quad_setup()), the column only for the 1/NB of the entries that stay
+                const int qr = __float2int_rd(__fmaf_rn(xy[u].y, (float)bc.h, -0.5f)) + 1;
                 const bool in = (i0 + u * 32 + lane < cnt) && qr >= bc.q0 && qr < bc.q1;
                 const unsigned bal = __ballot_sync(0xffffffffu, in);
                 if (in) {
-                    const unsigned key = (unsigned)((qr - bc.q0) * (bc.w + 1) + (q.w_low + 1));
+                    const int qc = __float2int_rd(__fmaf_rn(xy[u].x, (float)bc.w, -0.5f)) + 1;
+                    const unsigned key = (unsigned)((qr - bc.q0) * (bc.w + 1) + qc);
                     a[pos + __popc(bal & ((1u << lane) - 1u))] = ((W)key << bc.vb) | (W)id[u];
                 }
                 pos += __popc(bal);
@@ -338,7 +339,7 @@ __device__ void band_sort_body(const GfeatParams& p, const BandCtx& bc, W* a, W*
     }
     __syncthreads();
 
-    W* sorted = block_radix_sort<W>(a, b, bc.n, bc.vb, bc.kb, hist, tot);
+    W* sorted = block_radix_sort<W, kT>(a, b, bc.n, bc.vb, bc.kb, hist, tot);
 
     // sorted records: everything the reduce needs per contribution, so it never re-derives the quad
     int4* rec = p.rec + ((size_t)bc.b_idx * d.cams * d.L + bc.cl) * AP + bc.base;
@@ -391,13 +392,16 @@ __device__ void band_sort_body(const GfeatParams& p, const BandCtx& bc, W* a, W*
     }
 }
 
-// dynamic smem: hist[kSortWarps*kRadix] + tot[kRadix+32] + misc[16] + coff[n_chunks] + 2*kBandCap words
-inline size_t band_sort_smem_bytes(int n_chunks) {
-    return (size_t)(kSortWarps * kRadix + kRadix + 32 + 16 + ((n_chunks + 3) & ~3)) * 4 + (size_t)kBandCap * 2 * 4;
+// dynamic smem: hist[warps*kRadix] + tot[kRadix+32] + misc[16] + coff[n_chunks] + 2*cap words
+inline size_t band_sort_smem_bytes(int n_chunks, int threads, int cap) {
+    return (size_t)((threads / 32) * kRadix + kRadix + 32 + 16 + ((n_chunks + 3) & ~3)) * 4 + (size_t)cap * 2 * 4;
 }
 
-// grid (NB, cams*L, bs), block kSortThreads
-__global__ void __launch_bounds__(kSortThreads, 2) dfa_band_sort_kernel(const GfeatParams p) {
+// grid (NB, cams*L, bs), block kT threads (>= 256: the digit scan uses the first 8 warps); kCap packed words per
+// ping-pong half are kept in shared memory, longer bands sort in global memory
+template <int kT, int kCap>
+__global__ void __launch_bounds__(kT, (kT >= 512) ? 2 : 4) dfa_band_sort_kernel(const GfeatParams p) {
+    constexpr int kSortThreads = kT, kSortWarps = kT / 32, kBandCap = kCap;
     const Dims d = p.d;
     const int band = blockIdx.x, cl = blockIdx.y, b_idx = blockIdx.z;
     const int cam = cl / d.L;
@@ -469,17 +473,17 @@ __global__ void __launch_bounds__(kSortThreads, 2) dfa_band_sort_kernel(const Gf
     if (bc.vb + bc.kb <= 32) {
         if (bc.n <= kBandCap) {
             unsigned* a = reinterpret_cast<unsigned*>(data);
-            band_sort_body<unsigned>(p, bc, a, a + kBandCap, hist, tot, seg_band);
+            band_sort_body<unsigned, kT>(p, bc, a, a + kBandCap, hist, tot, seg_band);
         } else {
             unsigned* a = reinterpret_cast<unsigned*>(gbuf) + bc.base;
-            band_sort_body<unsigned>(p, bc, a, a + AP, hist, tot, seg_band);
+            band_sort_body<unsigned, kT>(p, bc, a, a + AP, hist, tot, seg_band);
         }
     } else {
         if (bc.n <= kBandCap / 2) {
             unsigned long long* a = reinterpret_cast<unsigned long long*>(data);
-            band_sort_body<unsigned long long>(p, bc, a, a + kBandCap / 2, hist, tot, seg_band);
+            band_sort_body<unsigned long long, kT>(p, bc, a, a + kBandCap / 2, hist, tot, seg_band);
         } else {
-            band_sort_body<unsigned long long>(p, bc, gbuf + bc.base, gbuf + AP + bc.base, hist, tot, seg_band);
+            band_sort_body<unsigned long long, kT>(p, bc, gbuf + bc.base, gbuf + AP + bc.base, hist, tot, seg_band);
         }
     }
 }

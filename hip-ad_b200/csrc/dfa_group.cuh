@@ -146,6 +146,15 @@ __global__ void __launch_bounds__(kW * 32, kMinCtas) dfa_group_kernel(const Grou
         const uint4 z = make_uint4(0u, 0u, 0u, 0u);
         for (long long i = z0 + tid; i < z1; i += kThreads) p.zero_ptr[i] = z;
     }
+    if (tid == 0) {
+        // The weights of the unit's pairs (L*G floats each, contiguous) are needed a few microseconds from now (phase 5
+        // forward, phase 7 backward) and come from DRAM: one bulk prefetch into L2 now takes that latency off the unit's
+        // critical path (cp.async.bulk.prefetch: no shared memory, no barrier to wait on).
+        const float* w0 = gc.weights + ((size_t)ba * NP + p0) * (L * G);
+        const unsigned bytes = (unsigned)n_mine * (unsigned)(L * G) * 4u;
+        if ((bytes & 15u) == 0)
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(w0), "r"(bytes) : "memory");
+    }
     load_level_table(tab, p.shapes, p.starts, cams * L);
 
     // ------------------------------------------------------------------ phase 1: visible pairs (ordered compaction)

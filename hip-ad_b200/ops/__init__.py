@@ -13,6 +13,7 @@ from .deformable_aggregation import (  # noqa: F401
     DeformableAggregationGroupFunction,
     FeatureMapsFormatFunction,
     KernelTimer,
+    aggregation_weights,
     deformable_aggregation_group,
     format_feature_levels,
     fused_deformable_aggregation,

@@ -359,6 +359,57 @@ def deformable_aggregation_group(mc_ms_feat, spatial_shape, scale_start_index, c
     return list(packed.split([l.shape[1] for l, _ in calls], dim=1))
 
 
+class AggregationWeightsFunction(Function):
+    """weights_fc logits -> the op's weight tensor in ONE pass each way: group softmax over cams*L*P
+    (blocks.py:196-208), the training attn-drop mask (blocks.py:209-212, drawn in the kernel instead of on the CPU) and the
+    permute(0,1,4,2,3,5).contiguous() copy (blocks.py:147-158).  apply(logits, cams, L, P, G, drop_p, seed, keep_mask)
+    with logits [bs, A, cams*L*P*G (any trailing shape)] -> weights [bs, A, P, cams, L, G]."""
+
+    @staticmethod
+    def forward(ctx, logits, cams, L, P, G, drop_p, seed, keep_mask):
+        lib = _lib.get()
+        _require_cuda(logits)
+        x = logits.contiguous().float()
+        bs, A = x.shape[:2]
+        if x.numel() != bs * A * cams * L * P * G:
+            raise ValueError("logits must hold bs*A*cams*L*P*G elements, got %s" % (tuple(x.shape),))
+        mask = keep_mask.contiguous().float() if keep_mask is not None else None
+        with torch.cuda.device(x.device):
+            w = torch.empty((bs, A, P, cams, L, G), dtype=torch.float32, device=x.device)
+            stats = torch.empty((bs, A, G, 2), dtype=torch.float32, device=x.device)
+            rc = lib.hipad_dfa_weights_forward(x.data_ptr(), w.data_ptr(), stats.data_ptr(),
+                                               mask.data_ptr() if mask is not None else None, int(seed), float(drop_p),
+                                               bs * A, cams, L, P, G, torch.cuda.current_stream().cuda_stream)
+        _lib.check(rc, "hipad_dfa_weights_forward")
+        ctx.save_for_backward(x, stats, mask if mask is not None else x.new_empty(0))
+        ctx.meta = (cams, L, P, G, float(drop_p), int(seed), mask is not None, logits.shape, logits.dtype)
+        return w
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g_w):
+        lib = _lib.get()
+        x, stats, mask = ctx.saved_tensors
+        cams, L, P, G, drop_p, seed, has_mask, shape, dtype = ctx.meta
+        gw = g_w.contiguous().float()
+        with torch.cuda.device(x.device):
+            g_x = torch.empty_like(x)
+            rc = lib.hipad_dfa_weights_backward(x.data_ptr(), stats.data_ptr(), gw.data_ptr(), g_x.data_ptr(),
+                                                mask.data_ptr() if has_mask else None, seed, drop_p, x.shape[0] * x.shape[1],
+                                                cams, L, P, G, torch.cuda.current_stream().cuda_stream)
+        _lib.check(rc, "hipad_dfa_weights_backward")
+        return g_x.reshape(shape).to(dtype), None, None, None, None, None, None, None
+
+
+def aggregation_weights(logits, cams, L, P, G, drop_p=0.0, seed=None, keep_mask=None):
+    """Softmaxed (and, when drop_p > 0, attn-dropped) aggregation weights [bs, A, P, cams, L, G] from raw ``weights_fc``
+    logits [bs, A, cams, L*P*G], differentiable.  ``seed`` defaults to a draw from torch's CPU generator (reproducible
+    under ``torch.manual_seed``, no device sync); ``keep_mask`` [bs, A, cams, P] overrides the in-kernel draw."""
+    if drop_p > 0 and seed is None and keep_mask is None:
+        seed = int(torch.empty((), dtype=torch.int64).random_().item())
+    return AggregationWeightsFunction.apply(logits, cams, L, P, G, drop_p, seed or 0, keep_mask)
+
+
 # import-compatibility alias (ops/__init__.py:3-4 of the reference exports both names; the A800
 # twin there is the same source bound to a second build, selected by GPU name string)
 DeformableAggregationFunctionA800 = DeformableAggregationFunction

@@ -252,6 +252,22 @@ int hipad_dfa_fused_forward_bf16(float *output, const uint16_t *mc_ms_feat,
                                  int num_scale, int num_anchors, int num_pts, int num_groups,
                                  void *stream);
 
+/* ---- weights producer of the aggregation module, one pass each way ("next" row f2, training half) ----
+ * Replaces the chain softmax over cams*L*P per group -> attn-drop mask (drawn on the CPU and copied over per call in the
+ * reference) -> permute(0,1,4,2,3,5).contiguous()  (models/blocks.py:196-212, 147-158) and its mirror image in the backward.
+ *   logits        [rows, cams, L, P, G]  raw weights_fc output, rows = bs*num_anchors
+ *   weights       [rows, P, cams, L, G]  what hipad_dfa_forward_* / hipad_dfa_group_forward consume
+ *   stats         [rows, G, 2]           (max, 1/sum) per group, saved for the backward (may be NULL in forward)
+ *   keep_mask     [rows, cams, P] or NULL: explicit keep mask (1 = keep); NULL = drawn in the kernel from
+ *                 (seed, row, cam, pt): keep iff uniform > drop_p, kept weights scaled by 1/(1-drop_p); drop_p = 0: none
+ * num_groups must divide 256. */
+int hipad_dfa_weights_forward(const float *logits, float *weights, float *stats, const float *keep_mask,
+                              unsigned long long seed, float drop_p, long long rows,
+                              int num_cams, int num_scale, int num_pts, int num_groups, void *stream);
+int hipad_dfa_weights_backward(const float *logits, const float *stats, const float *grad_weights, float *grad_logits,
+                               const float *keep_mask, unsigned long long seed, float drop_p, long long rows,
+                               int num_cams, int num_scale, int num_pts, int num_groups, void *stream);
+
 /* ---- feature_maps_format as one transposing pass ----
  * Replaces the cat + permute + flatten chain of feature_maps_format
  * (projects/mmdet3d_plugin/ops/__init__.py:74-103; two full copies of every feature map, the second a strided

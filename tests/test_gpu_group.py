@@ -319,3 +319,132 @@ def test_misaligned_sub_buffers_are_rejected_not_faulted(ops, cuda_lib):
                                           loc_ok.data_ptr(), w_ok.data_ptr(), *dims, s) == 0
     torch.cuda.synchronize()
     assert rel_err(out2.cpu().numpy(), out.cpu().numpy()) <= FP32_TOL
+
+
+def test_aggregate_layer_equals_module_by_module(ops):
+    """hipad_b200.aggregate_layer (the one-edit replacement of sparse_onedecoder.py:867-887) vs calling each module."""
+    import hipad_b200
+    torch.manual_seed(0)
+    kps_box = dict(type="SparseBox3DKeyPointsGenerator", num_learnable_pts=6,
+                   fix_scale=[[0, 0, 0], [0.45, 0, 0], [-0.45, 0, 0], [0, 0.45, 0], [0, -0.45, 0], [0, 0, 0.45], [0, 0, -0.45]])
+    kps_pts = dict(type="SparsePoint3DKeyPointsGenerator", embed_dims=256, num_sample=6, num_learnable_pts=3,
+                   fix_height=(0, 0.5, -0.5, 1, -1), ground_height=-1.84023)
+    mods = [hipad_b200.DeformableFeatureAggregation(embed_dims=256, num_groups=8, num_levels=4, num_cams=6, attn_drop=0.0,
+                                                    use_deformable_func=True, use_camera_embed=True, residual_mode="cat",
+                                                    kps_generator=k).cuda() for k in (kps_box, kps_pts)]
+    for m in mods:
+        torch.nn.init.normal_(m.weights_fc.weight, std=0.02)
+    bs = 2
+    levels = [torch.randn(bs, 6, 256, h, w, device="cuda") for h, w in SMALL_LV]
+    fm = hipad_b200.feature_maps_format(levels)
+    proj = torch.from_numpy(np.tile(H.projection_matrices((64, 112))[None], (bs, 1, 1, 1))).cuda()
+    metas = dict(projection_mat=proj, image_wh=torch.tensor([[112.0, 64.0]], device="cuda").repeat(bs, 6, 1))
+    rng = np.random.default_rng(0)
+    box = torch.from_numpy(np.concatenate([rng.uniform(-20, 20, (bs, 30, 2)), rng.uniform(-2, 0, (bs, 30, 1)),
+                                           rng.normal(0.5, 0.2, (bs, 30, 3)), np.tile([[[0.0, 1.0, 0, 0, 0]]], (bs, 30, 1))],
+                                          -1).astype(np.float32)).cuda()
+    line = torch.from_numpy(rng.uniform(-15, 30, (bs, 12, 12)).astype(np.float32)).cuda()
+    calls = [(mods[0], torch.randn(bs, 30, 256, device="cuda"), box, torch.randn(bs, 30, 256, device="cuda")),
+             (mods[1], torch.randn(bs, 12, 256, device="cuda"), line, torch.randn(bs, 12, 256, device="cuda"))]
+    with torch.enable_grad():
+        fm_g = [fm[0].clone().requires_grad_(True), fm[1], fm[2]]
+        outs = hipad_b200.aggregate_layer(calls, fm_g, metas)
+        sum(o.square().sum() for o in outs).backward()
+        fm_s = [fm[0].clone().requires_grad_(True), fm[1], fm[2]]
+        for m in mods:
+            m.zero_grad()
+        refs = [m(i, a, e, fm_s, metas) for m, i, a, e in calls]
+        sum(o.square().sum() for o in refs).backward()
+    for o, r in zip(outs, refs):
+        assert rel_err(o.detach().cpu().numpy(), r.detach().cpu().numpy()) <= FP32_TOL
+    assert rel_err(fm_g[0].grad.cpu().numpy(), fm_s[0].grad.cpu().numpy()) <= FP32_TOL
+
+
+# ------------------------------------------------------------------------------------- weights producer (row f2)
+def _reference_weights_chain(logits, cams, L, P, G, keep, drop_p):
+    """blocks.py:196-212 + :147-158 in torch ops: softmax over cams*L*P per group, mask, permute to the op's layout."""
+    bs, A = logits.shape[:2]
+    w = logits.reshape(bs, A, -1, G).softmax(dim=-2).reshape(bs, A, cams, L, P, G)
+    if drop_p > 0:
+        w = (keep[:, :, :, None, :, None] * w) / (1 - drop_p)
+    return w.permute(0, 1, 4, 2, 3, 5).contiguous()
+
+
+@pytest.mark.parametrize("shape", [(2, 37, 6, 4, 13, 8), (1, 5, 6, 4, 300, 8), (2, 9, 3, 4, 90, 4), (1, 3, 2, 3, 7, 1)])
+@pytest.mark.parametrize("drop_p", [0.0, 0.15])
+def test_weights_producer_matches_torch_chain(ops, shape, drop_p):
+    bs, A, cams, L, P, G = shape
+    g = torch.Generator(device="cuda").manual_seed(1)
+    logits = (torch.randn(bs, A, cams, L * P * G, device="cuda", generator=g) * 3).requires_grad_(True)
+    keep = (torch.rand(bs, A, cams, P, device="cuda", generator=g) > drop_p).float()
+    go = torch.randn(bs, A, P, cams, L, G, device="cuda", generator=g)
+    w = ops.aggregation_weights(logits, cams, L, P, G, drop_p, keep_mask=keep if drop_p > 0 else None)
+    w.backward(go)
+    got_g = logits.grad.clone()
+    logits.grad = None
+    ref = _reference_weights_chain(logits, cams, L, P, G, keep, drop_p)
+    ref.backward(go)
+    assert w.shape == ref.shape
+    assert rel_err(w.detach().cpu().numpy(), ref.detach().cpu().numpy()) <= 2e-6
+    assert rel_err(got_g.cpu().numpy(), logits.grad.cpu().numpy()) <= FP32_TOL
+
+
+def test_weights_producer_draws_its_mask_on_the_device(ops):
+    """In-kernel attn-drop: whole (cam, point) columns are dropped with probability p, kept ones scaled by 1/(1-p),
+    the same seed reproduces the same mask, forward and backward agree on it."""
+    bs, A, cams, L, P, G, p = 2, 200, 6, 4, 13, 8, 0.15
+    logits = torch.randn(bs, A, cams, L * P * G, device="cuda").requires_grad_(True)
+    base = ops.aggregation_weights(logits.detach(), cams, L, P, G, 0.0)
+    w1 = ops.aggregation_weights(logits, cams, L, P, G, p, seed=1234)
+    w2 = ops.aggregation_weights(logits.detach(), cams, L, P, G, p, seed=1234)
+    w3 = ops.aggregation_weights(logits.detach(), cams, L, P, G, p, seed=99)
+    assert torch.equal(w1.detach(), w2) and not torch.equal(w2, w3)
+    ratio = (w1.detach() / base)                                   # [bs, A, P, cams, L, G]: 0 or 1/(1-p), constant over (L, G)
+    kept = ratio > 0.5
+    assert torch.allclose(ratio[kept], torch.full_like(ratio[kept], 1 / (1 - p)), rtol=1e-5)
+    assert (kept == kept[..., :1, :1]).all()
+    frac = float(kept[..., 0, 0].float().mean())
+    assert abs(frac - (1 - p)) < 0.02
+    go = torch.randn_like(w1)
+    w1.backward(go)
+    keep = kept[..., 0, 0].permute(0, 1, 3, 2).float()             # [bs, A, cams, P]
+    l2 = logits.detach().clone().requires_grad_(True)
+    _reference_weights_chain(l2, cams, L, P, G, keep, p).backward(go)
+    assert rel_err(logits.grad.cpu().numpy(), l2.grad.cpu().numpy()) <= FP32_TOL
+
+
+def test_module_training_path_uses_the_fused_weights_producer(ops):
+    """Module forward + backward in training mode (attn_drop off for comparability) vs the reference chain of torch ops."""
+    import hipad_b200
+    torch.manual_seed(0)
+    kps = dict(type="SparseBox3DKeyPointsGenerator", num_learnable_pts=6,
+               fix_scale=[[0, 0, 0], [0.45, 0, 0], [-0.45, 0, 0], [0, 0.45, 0], [0, -0.45, 0], [0, 0, 0.45], [0, 0, -0.45]])
+    m = hipad_b200.DeformableFeatureAggregation(embed_dims=256, num_groups=8, num_levels=4, num_cams=6, attn_drop=0.0,
+                                                use_deformable_func=True, use_camera_embed=True, residual_mode="cat",
+                                                kps_generator=kps).cuda().train()
+    torch.nn.init.normal_(m.weights_fc.weight, std=0.05)
+    bs = 2
+    fm = hipad_b200.feature_maps_format([torch.randn(bs, 6, 256, h, w, device="cuda") for h, w in SMALL_LV])
+    proj = torch.from_numpy(np.tile(H.projection_matrices((64, 112))[None], (bs, 1, 1, 1))).cuda()
+    metas = dict(projection_mat=proj, image_wh=torch.tensor([[112.0, 64.0]], device="cuda").repeat(bs, 6, 1))
+    rng = np.random.default_rng(0)
+    box = torch.from_numpy(np.concatenate([rng.uniform(-20, 20, (bs, 30, 2)), rng.uniform(-2, 0, (bs, 30, 1)),
+                                           rng.normal(0.5, 0.2, (bs, 30, 3)), np.tile([[[0.0, 1.0, 0, 0, 0]]], (bs, 30, 1))],
+                                          -1).astype(np.float32)).cuda()
+    inst = torch.randn(bs, 30, 256, device="cuda", requires_grad=True)
+    emb = torch.randn(bs, 30, 256, device="cuda")
+    out = m(inst, box, emb, fm, metas)
+    out.square().sum().backward()
+    g1, gw1 = inst.grad.clone(), m.weights_fc.weight.grad.clone()
+    inst.grad = None
+    m.zero_grad()
+    # reference chain: _get_weights (torch softmax) + permute + the same op
+    kp = m.kps_generator(box, emb, inst)
+    w = m._get_weights(inst, emb, metas).permute(0, 1, 4, 2, 3, 5).contiguous()
+    p2d = m.project_points(kp, metas["projection_mat"], metas["image_wh"]).permute(0, 2, 3, 1, 4).reshape(bs, 30, 13, 6, 2)
+    f = ops.deformable_aggregation_function(*fm, p2d, w)
+    ref = torch.cat([m.output_proj(f), inst], dim=-1)
+    ref.square().sum().backward()
+    assert rel_err(out.detach().cpu().numpy(), ref.detach().cpu().numpy()) <= FP32_TOL
+    assert rel_err(g1.cpu().numpy(), inst.grad.cpu().numpy()) <= 2e-5
+    assert rel_err(gw1.cpu().numpy(), m.weights_fc.weight.grad.cpu().numpy()) <= 2e-5
