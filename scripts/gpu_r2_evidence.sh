@@ -24,4 +24,10 @@ timeout 900 ncu --set full --clock-control none --import-source on -k regex:dfa_
 ncu -i /tmp/full_group.ncu-rep --page raw --csv 2>/dev/null | gzip -9 > $OUT/full_layer_raw.csv.gz
 ncu -i /tmp/full_group.ncu-rep --page source --csv 2>/dev/null | gzip -9 > $OUT/full_layer_source.csv.gz
 python profiles/summarize_ncu.py /tmp/full_group.ncu-rep > $OUT/full_layer_summary.txt 2>&1
+python profiles/prof_percall.py 2 > $OUT/plain_percall.log 2>&1 && \
+timeout 900 ncu --set full --clock-control none -k regex:dfa_ --launch-skip 25 -c 25 -f -o /tmp/full_percall \
+    python profiles/prof_percall.py 2 > $OUT/ncu_percall.log 2>&1; echo "ncu percall rc=$?" | tee -a $OUT/status.txt
+ncu -i /tmp/full_percall.ncu-rep --page raw --csv 2>/dev/null | gzip -9 > $OUT/full_percall_raw.csv.gz
+python profiles/summarize_ncu.py /tmp/full_percall.ncu-rep > $OUT/full_percall_summary.txt 2>&1
+python profiles/ncu_traffic.py $OUT/full_percall_raw.csv.gz $OUT/dominant_kernel_traffic.json > /dev/null 2>> $OUT/ncu_percall.log
 cat $OUT/status.txt; du -sh $OUT
