@@ -153,6 +153,16 @@ __device__ __forceinline__ void unpack_bf16x8(const uint4& t, float (&v)[8]) {
     }
 }
 
+// Ticket increment with RELEASE semantics at gpu scope: orders the writes this thread has observed (its own and, through a
+// preceding __syncwarp / __syncthreads, those of the threads it synchronised with) before the increment.  Unlike
+// __threadfence() (MEMBAR.SC + CCTL.IVALL in every thread) it costs one MEMBAR in one thread and does NOT invalidate the
+// SM's L1, which the gather kernels live on.  Readers of the published data use ld.global.cg (L2) after an acquire fence.
+__device__ __forceinline__ int atomic_add_release_gpu(int* p, int v) {
+    int old;
+    asm volatile("atom.add.release.gpu.global.s32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
+    return old;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

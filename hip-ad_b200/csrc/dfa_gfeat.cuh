@@ -777,10 +777,9 @@ __global__ void __launch_bounds__(256, 2) dfa_gfeat_reduce_kernel(const GfeatPar
 #pragma unroll
                 for (int j = 0; j < NCH; ++j)
                     if (lm.act[j]) VecIO<float, V>::store(mine + lm.ch[j], acc[j]);
-                __threadfence();
                 __syncwarp();
                 int old = 0;
-                if (lane == 0) old = atomicAdd(p.unit_done + slot, 1);
+                if (lane == 0) old = atomic_add_release_gpu(p.unit_done + slot, 1);
                 old = __shfl_sync(0xffffffffu, old, 0);
                 if (old == parts - 1) {        // every part of this row is in memory: add them in part order
                     __threadfence();

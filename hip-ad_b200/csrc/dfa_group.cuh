@@ -529,9 +529,8 @@ __global__ void __launch_bounds__(kW * 32, kMinCtas) dfa_group_kernel(const Grou
                 for (int w = 0; w < kW; ++w) s += red[w * CPAD + ch];
                 mine[ch] = s;
             }
-            __threadfence();
             __syncthreads();
-            if (tid == 0) s_flag[0] = (atomicAdd(p.tickets + gc.row_begin + ba, 1) == S - 1) ? 1 : 0;
+            if (tid == 0) s_flag[0] = (atomic_add_release_gpu(p.tickets + gc.row_begin + ba, 1) == S - 1) ? 1 : 0;
             __syncthreads();
             if (s_flag[0]) {
                 __threadfence();
