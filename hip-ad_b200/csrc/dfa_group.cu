@@ -33,14 +33,18 @@ int launch_inst(const GroupParams& gp, int grid, size_t smem, cudaStream_t st) {
 // visibility / sort phases of some overlap the gather of others (measured, stage-2 layer: forward 92 vs 119 us,
 // backward 311 vs 336 us; HIPAD_DFA_GROUP_DEEP=1 selects the deep variant)
 template <bool kBwd>
-int dispatch(ElemType t, bool deep, const GroupParams& gp, int grid, size_t smem, cudaStream_t st) {
+int dispatch(ElemType t, int variant, const GroupParams& gp, int grid, size_t smem, cudaStream_t st) {
+    // variant 0: deep pipeline, 4 CTAs/SM; 1: shallow, 6 CTAs/SM (<= 80 registers); 2: shallow, 8 CTAs/SM (64 registers)
     if (t == kF32) {
         if (gp.C == 128) return launch_inst<float, 4, 1, kBwd, 4, 2, 5>(gp, grid, smem, st);
-        if (gp.C == 256) return deep ? launch_inst<float, 4, 2, kBwd, 4, 2, 4>(gp, grid, smem, st)
-                                     : launch_inst<float, 4, 2, kBwd, 4, 1, 6>(gp, grid, smem, st);
+        if (gp.C == 256) {
+            if (variant == 0) return launch_inst<float, 4, 2, kBwd, 4, 2, 4>(gp, grid, smem, st);
+            if (variant == 2) return launch_inst<float, 4, 2, kBwd, 4, 1, 8>(gp, grid, smem, st);
+            return launch_inst<float, 4, 2, kBwd, 4, 1, 6>(gp, grid, smem, st);
+        }
     } else {
-        if (gp.C == 256) return deep ? launch_inst<__nv_bfloat16, 8, 1, kBwd, 4, 4, 4>(gp, grid, smem, st)
-                                     : launch_inst<__nv_bfloat16, 8, 1, kBwd, 4, 2, 5>(gp, grid, smem, st);
+        if (gp.C == 256) return variant == 0 ? launch_inst<__nv_bfloat16, 8, 1, kBwd, 4, 4, 4>(gp, grid, smem, st)
+                                             : launch_inst<__nv_bfloat16, 8, 1, kBwd, 4, 2, 5>(gp, grid, smem, st);
     }
     return -2;
 }
@@ -132,8 +136,11 @@ int launch_group_sample(bool bwd, ElemType t, const GroupParams& gp, long long u
     g.so = group_smem_layout(bwd, gp.ps_max, nch * 32 * V, kw);
     const size_t smem = (size_t)g.so.total;
     if (smem > kSampleSmemBudget) return -2;
-    const bool deep = hipad_env_int("HIPAD_DFA_GROUP_DEEP", 0) != 0;
-    return bwd ? dispatch<true>(t, deep, g, (int)units, smem, st) : dispatch<false>(t, deep, g, (int)units, smem, st);
+    // measured (stage-2 layer, f32): forward 82 us at 8 CTAs/SM vs 89 at 6 (bs=4: 257 vs 296); the backward needs more
+    // registers (64 spills inside its epilogue) and is faster at 6 (118 vs 129 us)
+    int variant = hipad_env_int("HIPAD_DFA_GROUP_CTAS", bwd ? 6 : 8) >= 8 ? 2 : 1;
+    if (hipad_env_int("HIPAD_DFA_GROUP_DEEP", 0) != 0) variant = 0;
+    return bwd ? dispatch<true>(t, variant, g, (int)units, smem, st) : dispatch<false>(t, variant, g, (int)units, smem, st);
 }
 
 int launch_group_forward(const GroupFwdArgs& a) {
