@@ -108,9 +108,12 @@ WorkspaceLayout workspace_layout(int bs, int cams, int num_feat, int C, int L, i
 
 template <typename T, int V, int NCH>
 int launch_reduce_nq(const GfeatParams& gp, cudaStream_t st) {
-#define HIPAD_NQ(NQ_)                                                                          \
-    case NQ_:                                                                                  \
-        dfa_gfeat_reduce_kernel<T, V, NCH, NQ_><<<kReduceCtas, 256, 0, st>>>(gp);              \
+    // light variant: 4 contributions in flight per warp, <= 64 registers, 4 CTAs per SM (HIPAD_DFA_REDUCE_LIGHT)
+    const bool light = hipad_env_int("HIPAD_DFA_REDUCE_LIGHT", 0) != 0;
+#define HIPAD_NQ(NQ_)                                                                                      \
+    case NQ_:                                                                                              \
+        if (light) dfa_gfeat_reduce_kernel<T, V, NCH, NQ_, 3><<<148 * 3, 256, 0, st>>>(gp);              \
+        else dfa_gfeat_reduce_kernel<T, V, NCH, NQ_, 2><<<kReduceCtas, 256, 0, st>>>(gp);                  \
         break
     switch (gp.tiny_ok ? gp.d.C / 32 : 0) {
         HIPAD_NQ(0); HIPAD_NQ(1); HIPAD_NQ(2); HIPAD_NQ(4); HIPAD_NQ(8);

@@ -39,7 +39,7 @@ constexpr int kMaxBands = 32;
 constexpr int kScanUnroll = 8;           // independent loads in flight per lane in the band kernel's scans
 constexpr int kSegScale = 8;             // ints of segment table per feature row (upper bound, see seg_offset)
 constexpr int kClassifyThreads = 256;    // rows classified per CTA (one thread each)
-constexpr int kReduceCtas = 148 * 2;     // persistent CTAs (8 warps, 2 per SM) of the reduce kernel
+constexpr int kReduceCtas = 148 * 2;     // persistent CTAs (8 warps, 2 per SM; 4 per SM for the light variant) of the reduce kernel
 constexpr int kTinyRow = 8;              // contributions up to which a row is summed by a quarter warp
 constexpr int kPart = 64;                // contributions per part item (longer rows are split into parts); measured on the
                                          // stage-2 det / map / plan calls: 32 -> 46 / 76 / 81 us, 64 -> 45 / 68 / 65 us, 128 -> 49 / 73 / 66 us
@@ -543,11 +543,13 @@ __device__ __forceinline__ void row_ctx_from_entry(RowCtx<V, NCH>& cx, const Lan
 // batch is padded with copies of the range's last contribution at coefficient 0, so a typical row (a
 // handful of contributions) costs one memory round trip instead of one per contribution.  Addresses are
 // one 64-bit base per tensor plus 32-bit byte offsets (the loop is issue-bound otherwise).
-template <int V, int NCH>
+template <int V, int NCH, int kBatchCap>
 __device__ __forceinline__ void accumulate_row(const RowCtx<V, NCH>& cx, int c_lo, int c_hi, float (&acc)[NCH][V]) {
-    // contributions whose loads are in flight together: 64 data registers per lane
+    // contributions whose loads are in flight together: 64 data registers per lane (kBatchCap = 4: 32, for the
+    // light variant of the kernel that keeps 4 CTAs per SM resident)
     constexpr int kRegsPer = NCH * (V + 1);
-    constexpr int kReduceBatch = (kRegsPer <= 10) ? 8 : (kRegsPer <= 20) ? 4 : (kRegsPer <= 40) ? 2 : 1;
+    constexpr int kBatch0 = (kRegsPer <= 10) ? 8 : (kRegsPer <= 20) ? 4 : (kRegsPer <= 40) ? 2 : 1;
+    constexpr int kReduceBatch = kBatch0 < kBatchCap ? kBatch0 : kBatchCap;
     constexpr bool kConstChunks = (V > 1);   // vector path: chunk j sits j*32*V channels after chunk 0
     const int lane = threadIdx.x & 31;
     for (int v0 = c_lo; v0 < c_hi; v0 += 32) {
@@ -700,8 +702,9 @@ __global__ void __launch_bounds__(kClassifyThreads) dfa_row_classify_kernel(cons
 //               channels (i*8+s)*4.. of every 32-channel chunk i < NQ = C/32; (C/G) % 32 == 0).  Such rows are
 //               pure latency (entry -> records -> grad_out rows); the lever is rows in flight per SM.
 // The next item's index and its list entry are fetched while the current item is processed.
-template <typename T, int V, int NCH, int NQ>
-__global__ void __launch_bounds__(256, 2) dfa_gfeat_reduce_kernel(const GfeatParams p) {
+template <typename T, int V, int NCH, int NQ, int kMinCtas>
+__global__ void __launch_bounds__(256, kMinCtas) dfa_gfeat_reduce_kernel(const GfeatParams p) {
+    constexpr int kBatchCap = (kMinCtas >= 3) ? 4 : 8;
     const Dims d = p.d;
     const int lane = threadIdx.x & 31, sub = lane & 7, quarter = lane >> 3;
     const int n_parts = p.counters[0];
@@ -770,7 +773,7 @@ __global__ void __launch_bounds__(256, 2) dfa_gfeat_reduce_kernel(const GfeatPar
             for (int j = 0; j < NCH; ++j)
 #pragma unroll
                 for (int e = 0; e < V; ++e) acc[j][e] = 0.f;
-            accumulate_row<V, NCH>(cx, c_lo, c_hi, acc);
+            accumulate_row<V, NCH, kBatchCap>(cx, c_lo, c_hi, acc);
             bool write_row = parts == 1;
             if (parts > 1) {
                 float* mine = p.partial + (size_t)(slot + u) * d.C;
