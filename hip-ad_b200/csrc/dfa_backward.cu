@@ -258,21 +258,18 @@ int launch_group_backward(const GroupBwdArgs& a) {
             int rc = fill_group_params(gpk, pl, a.calls, a.ncalls, d.bs, d.cams, d.num_feat, d.C, d.G,
                                        ids.a_total * d.C, nullptr, a.grad_out);
             if (rc != 0) return finish(rc);
-            // a launch too small to fold the dense zero fill in (the ego call: one output row): the fill gets the
-            // caller's stream to itself and the sample kernel joins the sort chain on the helper stream (it writes
-            // grad_weights / grad_sampling_location only), so the call costs the fill, not the sum of six launches
-            cudaStream_t sample_stream = a.stream;
             if (want_zero) {
+                // (measured and not kept: giving a launch too small to fold the fill in -- the ego call -- the helper
+                // stream for its sample kernel as well: 45 vs 41 us; in a group the ego call costs nothing anyway)
                 if (vec_ok && pl.units >= 2 * 148 && !a.separate_zero_fill) {
                     gpk.zero_ptr = reinterpret_cast<uint4*>(a.g_feat);
                     gpk.zero_n16 = (long long)(gfeat_bytes / 16);
-                } else {
-                    if (int e = separate_zero()) return finish(e);
-                    if (side != nullptr) sample_stream = chain;
+                } else if (int e = separate_zero()) {
+                    return finish(e);
                 }
                 zero_done = true;
             }
-            rc = launch_group_sample(true, a.type, gpk, pl.units, sample_stream);
+            rc = launch_group_sample(true, a.type, gpk, pl.units, a.stream);
             if (rc != 0) return finish(rc);
         } else {
             for (int k = 0; k < a.ncalls; ++k) {

@@ -43,8 +43,11 @@ int dispatch(ElemType t, int variant, const GroupParams& gp, int grid, size_t sm
             return launch_inst<float, 4, 2, kBwd, 4, 1, 6>(gp, grid, smem, st);
         }
     } else {
-        if (gp.C == 256) return variant == 0 ? launch_inst<__nv_bfloat16, 8, 1, kBwd, 4, 4, 4>(gp, grid, smem, st)
-                                             : launch_inst<__nv_bfloat16, 8, 1, kBwd, 4, 2, 5>(gp, grid, smem, st);
+        if (gp.C == 256) {
+            if (variant == 0) return launch_inst<__nv_bfloat16, 8, 1, kBwd, 4, 4, 4>(gp, grid, smem, st);
+            if (variant == 2) return launch_inst<__nv_bfloat16, 8, 1, kBwd, 4, 2, 8>(gp, grid, smem, st);
+            return launch_inst<__nv_bfloat16, 8, 1, kBwd, 4, 2, 5>(gp, grid, smem, st);
+        }
     }
     return -2;
 }
@@ -52,7 +55,7 @@ int dispatch(ElemType t, int variant, const GroupParams& gp, int grid, size_t sm
 
 bool group_kernel_supported(ElemType t, int C, int L, int G, int cams) {
     if (hipad_env_int("HIPAD_DFA_GROUP_KERNEL", 1) == 0) return false;      // A/B knob: round-1 kernels only
-    if (L != kGroupL || G < 1 || G > kGroupMaxG || C % G != 0 || cams * L > kMaxCamLevels) return false;
+    if (L != kGroupL || G < 1 || G > kGroupMaxG || (G & (G - 1)) != 0 || C % G != 0 || cams * L > kMaxCamLevels) return false;
     const int V = (t == kF32) ? 4 : 8;
     const int gd = C / G;
     if (gd % V != 0) return false;

@@ -46,7 +46,7 @@ struct GroupCall {
 };
 
 struct GroupSmem {
-    int tab, wcnt, flag, vis, lxy, lpair, key, mask, lhlw, sorted, qof, qstart, gxy, qrows, qtab, total;
+    int tab, wcnt, flag, vis, lxy, lpair, key, mask, lhlw, woff, sorted, qof, qstart, gxy, qrows, qtab, total;
 };
 __host__ __device__ inline GroupSmem group_smem_layout(bool bwd, int ps_max, int cpad, int warps) {
     GroupSmem o;
@@ -61,7 +61,8 @@ __host__ __device__ inline GroupSmem group_smem_layout(bool bwd, int ps_max, int
     o.lpair = take(ps_max * 2);
     o.key = take(items * 4);
     o.mask = take(items);
-    o.lhlw = take(items * 8);
+    o.lhlw = take(items * (bwd ? 8 : 16));   // backward: (lh, lw) per item; forward: its four masked bilinear terms
+    o.woff = take(items * 2);
     o.sorted = take(items * 2);
     o.qof = take(items * 2);
     o.qstart = take((items + 1) * 2);
@@ -129,6 +130,8 @@ __global__ void __launch_bounds__(kW * 32, kMinCtas) dfa_group_kernel(const Grou
     unsigned* s_key = reinterpret_cast<unsigned*>(smem_raw + so.key);
     unsigned char* s_mask = smem_raw + so.mask;
     float2* s_lhlw = reinterpret_cast<float2*>(smem_raw + so.lhlw);
+    float4* s_c4 = reinterpret_cast<float4*>(smem_raw + so.lhlw);
+    unsigned short* s_woff = reinterpret_cast<unsigned short*>(smem_raw + so.woff);
     unsigned short* s_sorted = reinterpret_cast<unsigned short*>(smem_raw + so.sorted);
     unsigned short* s_qof = reinterpret_cast<unsigned short*>(smem_raw + so.qof);
     unsigned short* s_qstart = reinterpret_cast<unsigned short*>(smem_raw + so.qstart);
@@ -221,7 +224,13 @@ __global__ void __launch_bounds__(kW * 32, kMinCtas) dfa_group_kernel(const Grou
             const Quad q = quad_setup(xy.x, xy.y, t[0], t[1]);
             key = ((unsigned)cam << 26) | ((unsigned)(q.h_low + 1) << 13) | (unsigned)(q.w_low + 1);
             s_mask[l * n_pad + i] = (unsigned char)((int)q.ok1 | ((int)q.ok2 << 1) | ((int)q.ok3 << 2) | ((int)q.ok4 << 3));
-            s_lhlw[l * n_pad + i] = make_float2(q.lh, q.lw);
+            if constexpr (kBwd) {
+                s_lhlw[l * n_pad + i] = make_float2(q.lh, q.lw);
+            } else {
+                s_c4[l * n_pad + i] = make_float4(q.ok1 ? q.hh * q.hw : 0.f, q.ok2 ? q.hh * q.lw : 0.f,
+                                                  q.ok3 ? q.lh * q.hw : 0.f, q.ok4 ? q.lh * q.lw : 0.f);
+            }
+            s_woff[l * n_pad + i] = (unsigned short)(((int)l_pair[i] * L + l) * G);     // < 96 * 4 * 8
         }
         s_key[l * n_pad + i] = key;
     }
@@ -358,21 +367,19 @@ __global__ void __launch_bounds__(kW * 32, kMinCtas) dfa_group_kernel(const Grou
         }
         if constexpr (!kBwd) {
             // table[quad][group] = sum over the quad's items of (bilinear term of corner k) * weight[group], k = 1..4
-            for (int task = tid; task < nq * G; task += kThreads) {
-                const int qi = task / G, g = task - qi * G;
+            const int lg2 = 31 - __clz(G);                        // G is a power of two (host-checked)
+            for (int task = tid; task < (nq << lg2); task += kThreads) {
+                const int qi = task >> lg2, g = task & (G - 1);
                 const int r0 = s_qstart[qc0 + qi], r1 = s_qstart[qc0 + qi + 1];
                 float4 tsum = make_float4(0.f, 0.f, 0.f, 0.f);
                 for (int r = r0; r < r1; ++r) {
                     const int it = s_sorted[r];
-                    const int l = level_of(it), i = it - l * n_pad;
-                    const float2 f = s_lhlw[it];
-                    const float hh = 1.f - f.x, hw = 1.f - f.y;          // same expressions as quad_setup()
-                    const int m = s_mask[it];
-                    const float wv = __ldg(w_unit + ((size_t)l_pair[i] * L + l) * G + g);
-                    tsum.x += ((m & 1) ? hh * hw : 0.f) * wv;
-                    tsum.y += ((m & 2) ? hh * f.y : 0.f) * wv;
-                    tsum.z += ((m & 4) ? f.x * hw : 0.f) * wv;
-                    tsum.w += ((m & 8) ? f.x * f.y : 0.f) * wv;
+                    const float4 c4 = s_c4[it];
+                    const float wv = __ldg(w_unit + (s_woff[it] + g));
+                    tsum.x = __fmaf_rn(c4.x, wv, tsum.x);
+                    tsum.y = __fmaf_rn(c4.y, wv, tsum.y);
+                    tsum.z = __fmaf_rn(c4.z, wv, tsum.z);
+                    tsum.w = __fmaf_rn(c4.w, wv, tsum.w);
                 }
                 q_tab[qi * kGroupMaxG + g] = tsum;
             }
@@ -474,7 +481,7 @@ __global__ void __launch_bounds__(kW * 32, kMinCtas) dfa_group_kernel(const Grou
             const int ra = s_qstart[qc0], rb = s_qstart[qc0 + nq];
             for (int r = ra + tid; r < rb; r += kThreads) {
                 const int it = s_sorted[r];
-                const int l = level_of(it), i = it - l * n_pad;
+                const int l = level_of(it);
                 const int qi = (int)s_qof[it] - qc0;
                 const int* t = tab + ((int)(s_key[it] >> 26) * L + l) * 3;
                 const float2 f = s_lhlw[it];
@@ -488,7 +495,7 @@ __global__ void __launch_bounds__(kW * 32, kMinCtas) dfa_group_kernel(const Grou
                 const float x3 = (m & 4) ? -ig.lh * W_ : 0.f, x4 = (m & 8) ? ig.lh * W_ : 0.f;
                 const float y1 = (m & 1) ? -ig.hw * H_ : 0.f, y2 = (m & 2) ? -ig.lw * H_ : 0.f;
                 const float y3 = (m & 4) ? ig.hw * H_ : 0.f, y4 = (m & 8) ? ig.lw * H_ : 0.f;
-                const size_t woff = ((size_t)l_pair[i] * L + l) * G;
+                const size_t woff = s_woff[it];
                 const float* wsrc = w_unit + woff;
                 float* gdst = gc.g_w + ((size_t)ba * NP + p0) * (L * G) + woff;
                 float gx = 0.f, gy = 0.f;
