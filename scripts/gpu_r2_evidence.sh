@@ -14,6 +14,7 @@ for cfg in "1 f32 352x640 480" "4 f32 352x640 480" "8 f32 352x640 480" "1 bf16 3
 done
 timeout 600 python profiles/run_sweep.py 1 > $OUT/sweep_configs3_bs1.md 2> $OUT/sweep1.err; echo "sweep bs1 rc=$?" | tee -a $OUT/status.txt
 timeout 600 python profiles/run_sweep.py 4 > $OUT/sweep_configs3_bs4.md 2> $OUT/sweep4.err; echo "sweep bs4 rc=$?" | tee -a $OUT/status.txt
+timeout 600 python profiles/run_sweep.py 8 > $OUT/sweep_configs3_bs8.md 2> $OUT/sweep8.err; echo "sweep bs8 rc=$?" | tee -a $OUT/status.txt
 timeout 600 python harness/parity_report.py > $OUT/decoder_parity.json 2> $OUT/decoder_parity.err; echo "decoder parity rc=$?" | tee -a $OUT/status.txt
 python bench.py --steps 2 --warmup 3 --skip-e2e --skip-cpu --skip-decoder --skip-ref-op --no-graph --streams 1 > $OUT/plain_for_ncu.log 2>&1 && \
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:dfa_ -c 600 --csv --log-file $OUT/ncu_launch_list_bench_steps2.csv \
