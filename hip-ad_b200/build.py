@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(LIB_DIR, "libhipad_dfa.so")
 OBJ_DIR = os.path.join(LIB_DIR, "obj")
 SOURCES = ["dfa_forward.cu", "dfa_backward.cu", "dfa_group.cu", "dfa_api.cu", "dfa_format.cu", "dfa_weights.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-Xcompiler", "-fPIC"]
+              "-Xcompiler", "-fPIC"] + os.environ.get("HIPAD_DFA_NVCC_EXTRA", "").split()
 
 
 def _fingerprint():

@@ -55,7 +55,7 @@ constexpr size_t kAlign = 256;
 inline size_t align_up(size_t v) { return (v + kAlign - 1) / kAlign * kAlign; }
 
 struct WorkspaceLayout {
-    size_t vis_id, vis_xy, vis_cnt, band_cnt, rec, recw, seg, cursor, sortbuf, part_list, tiny_list, partial, unit_done, counters, total;
+    size_t vis_key, chunk_cum, ghist, ghist_bytes, rec, recw, seg, cursor, sortbuf, part_list, tiny_list, partial, unit_done, counters, total;
     size_t partial_slots;
     int seg_stride, n_chunks;
 };
@@ -81,13 +81,13 @@ WorkspaceLayout workspace_layout(int bs, int cams, int num_feat, int C, int L, i
     WorkspaceLayout w;
     const size_t n_cl = (size_t)cams * L, AP = (size_t)n_ids;
     w.n_chunks = (int)(AP / kVisChunk);
-    // band tables of a bucket occupy [8*start, 8*(start + h*w)) (dfa_gfeat.cuh, seg_offset)
+    // the segment table of a bucket occupies [kSegScale*start, kSegScale*(start + h*w)) (dfa_gfeat.cuh, seg_offset)
     w.seg_stride = (int)((size_t)kSegScale * num_feat);
     size_t off = 0;
-    w.vis_id = off;  off += align_up((size_t)bs * cams * AP * sizeof(int));
-    w.vis_xy = off;  off += align_up((size_t)bs * cams * AP * sizeof(float2));
-    w.vis_cnt = off; off += align_up((size_t)bs * cams * w.n_chunks * sizeof(int));
-    w.band_cnt = off; off += align_up((size_t)bs * cams * w.n_chunks * L * kMaxBands * sizeof(int));
+    w.vis_key = off; off += align_up((size_t)bs * n_cl * AP * sizeof(unsigned long long));
+    w.chunk_cum = off; off += align_up((size_t)bs * cams * w.n_chunks * L * kCum * sizeof(int));
+    w.ghist_bytes = (size_t)bs * n_cl * kFine * sizeof(int);
+    w.ghist = off;   off += align_up(w.ghist_bytes);
     w.rec = off;     off += align_up((size_t)bs * n_cl * AP * sizeof(int4));
     w.recw = off;    off += align_up((size_t)bs * n_cl * AP * G * sizeof(float));
     w.seg = off;     off += align_up((size_t)bs * w.seg_stride * sizeof(int));
@@ -323,10 +323,9 @@ int launch_group_backward(const GroupBwdArgs& a) {
     gp.n_ids = (int)ids.n_ids;
     gp.A_total = (int)ids.a_total;
     gp.grad_out = a.grad_out; gp.g_feat = a.g_feat;
-    gp.vis_id = reinterpret_cast<int*>(ws + wl.vis_id);
-    gp.vis_xy = reinterpret_cast<float2*>(ws + wl.vis_xy);
-    gp.vis_cnt = reinterpret_cast<int*>(ws + wl.vis_cnt);
-    gp.band_cnt = reinterpret_cast<int*>(ws + wl.band_cnt);
+    gp.vis_key = reinterpret_cast<unsigned long long*>(ws + wl.vis_key);
+    gp.chunk_cum = reinterpret_cast<int*>(ws + wl.chunk_cum);
+    gp.ghist = reinterpret_cast<int*>(ws + wl.ghist);
     gp.rec = reinterpret_cast<int4*>(ws + wl.rec);
     gp.recw = reinterpret_cast<float*>(ws + wl.recw);
     gp.seg = reinterpret_cast<int*>(ws + wl.seg);
@@ -345,16 +344,22 @@ int launch_group_backward(const GroupBwdArgs& a) {
     gp.d = d;
     gp.seg_stride = wl.seg_stride;
     gp.n_chunks = wl.n_chunks;
-    // enough bands for ~2 sort CTAs per SM, whatever the batch size; twice that for long sample lists, where a band
-    // CTA's cost is the pass over its camera's visible samples (measured, stage-2 map / plan: 24 bands 36 / 40 us
-    // against 42 / 46 us with 12-16; the det call, A*P = 11 700, is 2 us faster with 12)
-    const int buckets = d.cams * d.L * d.bs;
-    int nb = (2 * 148) / buckets;
-    if (ids.n_ids >= 24000) nb *= 2;
-    gp.NB = nb < 1 ? 1 : (nb > kMaxBands ? kMaxBands : nb);
+    // Band CTAs launched per (cam, level) bucket; a bucket uses ceil(samples / band_target) of them (the rest exit
+    // after reading the bucket's histogram), so the launch covers the busiest camera and quiet cameras cost little
+    gp.band_target = 768;
+    {
+        const long long most = (ids.n_ids + gp.band_target - 1) / gp.band_target;     // every sample seen by one camera
+        gp.NB = (int)(most < 1 ? 1 : (most > kMaxBands ? kMaxBands : most));
+    }
     {   // A/B knobs
         const int fb = hipad_env_int("HIPAD_DFA_BANDS", 0);
         if (fb >= 1 && fb <= kMaxBands) gp.NB = fb;
+        const int bt = hipad_env_int("HIPAD_DFA_BAND_TARGET", 0);
+        if (bt >= 64) {
+            gp.band_target = bt;
+            const long long most = (ids.n_ids + bt - 1) / bt;
+            if (fb < 1) gp.NB = (int)(most < 1 ? 1 : (most > kMaxBands ? kMaxBands : most));
+        }
         const int tm = hipad_env_int("HIPAD_DFA_TINY_MAX", kTinyRow);
         gp.tiny_max = tm < 1 ? 1 : (tm > kTinyRow ? kTinyRow : tm);
     }
@@ -362,13 +367,16 @@ int launch_group_backward(const GroupBwdArgs& a) {
     gp.tiny_ok = (ks_g.vector && (d.C == 32 || d.C == 64 || d.C == 128 || d.C == 256) && (d.C / d.G) % 32 == 0 &&
                   hipad_env_int("HIPAD_DFA_TINY", 1) != 0) ? 1 : 0;
     if (a.stage_mask & 2) {
+        cudaError_t e = cudaMemsetAsync(gp.ghist, 0, wl.ghist_bytes, chain);     // the compaction kernel adds to it
+        if (e != cudaSuccess) return finish((int)e);
         dfa_vis_compact_kernel<<<dim3((unsigned)wl.n_chunks, (unsigned)d.cams, (unsigned)d.bs), kVisThreads, 0,
                                  chain>>>(gp);
-        cudaError_t e = cudaGetLastError();
+        e = cudaGetLastError();
         if (e != cudaSuccess) return finish((int)e);
-        // 512-thread sort CTAs; HIPAD_DFA_SORT_THREADS=256 selects 256-thread CTAs with half the shared memory
-        // (measured slower on the stage-2 layer, 116 vs 93 us: the band CTA's cost is the walk over its camera's list)
-        const bool wide = hipad_env_int("HIPAD_DFA_SORT_THREADS", 512) >= 512;
+        // 256-thread sort CTAs (4 per SM) of ~768 samples; HIPAD_DFA_SORT_THREADS=512 selects 512-thread CTAs with twice
+        // the shared memory.  Every phase of a band CTA is a chain of memory round trips, so what pays is CTAs per SM:
+        // stage-2 layer, compaction + sort, bs = 1 / 4: 256 threads x 768 samples 60 / 124 us, 512 x 1536 62 / 140 us
+        const bool wide = hipad_env_int("HIPAD_DFA_SORT_THREADS", 256) >= 512;
         const dim3 sgrid((unsigned)gp.NB, (unsigned)(d.cams * d.L), (unsigned)d.bs);
         if (wide) {
             const size_t sort_smem = band_sort_smem_bytes(wl.n_chunks, 512, 8192);
@@ -403,3 +411,15 @@ int launch_group_backward(const GroupBwdArgs& a) {
 }
 
 }  // namespace hipad
+
+#ifdef HIPAD_DFA_TRACE
+// development builds: copy (and clear) the per-CTA phase trace of this translation unit's kernels
+extern "C" int hipad_dfa_trace_read_gfeat(long long* host, long long count) {
+    cudaDeviceSynchronize();
+    const int rc = (int)cudaMemcpyFromSymbol(host, hipad::g_trace, sizeof(long long) * (size_t)count);
+    void* sym = nullptr;
+    cudaGetSymbolAddress(&sym, hipad::g_trace);
+    cudaMemset(sym, 0, sizeof(hipad::g_trace));
+    return rc;
+}
+#endif

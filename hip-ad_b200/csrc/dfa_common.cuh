@@ -169,6 +169,42 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
+// Per-CTA phase trace of one kernel (development builds only: HIPAD_DFA_NVCC_EXTRA=-DHIPAD_DFA_TRACE python build.py).
+// One trace array per translation unit (read back with hipad_dfa_trace_read(unit, ...)).
+// slot 0 = globaltimer at entry, 1 = SM id, 2.. = clock64 at the marks, read back with hipad_dfa_trace_read().
+#ifdef HIPAD_DFA_TRACE
+constexpr int kTraceSlots = 14, kTraceCtas = 1 << 14;
+static __device__ long long g_trace[kTraceCtas * kTraceSlots];
+__device__ __forceinline__ void trace_mark(int cta, int slot, long long v) {
+    if (threadIdx.x == 0 && cta < kTraceCtas) g_trace[cta * kTraceSlots + slot] = v;
+}
+__device__ __forceinline__ long long trace_globaltimer() {
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ int trace_smid() {
+    int s;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(s));
+    return s;
+}
+#define DFA_TRACE(cta, slot) trace_mark((cta), (slot), clock64())
+#define DFA_TRACE_V(cta, slot, v) trace_mark((cta), (slot), (long long)(v))
+#define DFA_TRACE_END(cta, slot) trace_mark((cta), (slot), trace_globaltimer())
+#define DFA_TRACE_DECL(name) long long name = 0
+#define DFA_TRACE_ACC(name, t0) name += clock64() - (t0)
+#define DFA_TRACE_NOW(name) const long long name = clock64()
+#define DFA_TRACE_BEGIN(cta) do { trace_mark((cta), 0, trace_globaltimer()); trace_mark((cta), 1, trace_smid()); } while (0)
+#else
+#define DFA_TRACE(cta, slot) ((void)0)
+#define DFA_TRACE_V(cta, slot, v) ((void)0)
+#define DFA_TRACE_BEGIN(cta) ((void)0)
+#define DFA_TRACE_END(cta, slot) ((void)0)
+#define DFA_TRACE_DECL(name) ((void)0)
+#define DFA_TRACE_ACC(name, t0) ((void)0)
+#define DFA_TRACE_NOW(name) ((void)0)
+#endif
+
 // (cam,level) table in shared memory: {h, w, start} per entry
 __device__ __forceinline__ void load_level_table(int* tab, const int* __restrict__ shapes,
                                                  const int* __restrict__ starts, int n_cl) {

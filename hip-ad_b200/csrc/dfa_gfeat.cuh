@@ -8,15 +8,18 @@
 //       sample-major backward kernel has enough CTAs the fill is folded into that kernel instead (its
 //       stores ride under the gather latency of that kernel, which leaves the HBM write path idle).
 //   dfa_vis_compact_kernel  per (b, cam, chunk of 1024 samples): ordered compaction of the visible
-//       samples (id + location).  Many small CTAs; the only pass that touches every location.
-//   dfa_band_sort_kernel    per (b, cam, level, BAND of quad rows): picks the visible samples whose quad
-//       falls into its band (ordered), radix-sorts (quad key, sample) words in shared memory (stable LSD,
-//       __match_any_sync ranks), and emits 16-byte records {sample, anchor, lh, lw} in sorted order plus
-//       the band's segment table seg[key] = first record with key' >= key.  A (cam, level) bucket is
-//       split into up to 16 bands so that ~2 CTAs per SM run even at batch size 1 (the previous
-//       one-CTA-per-bucket sort left 124 of 148 SMs idle).  Where a band's records land inside the
-//       bucket's record array is decided by an integer atomic cursor; the order INSIDE a key segment is
-//       the stable sample order, which is all the summation order depends on.
+//       samples; per level it writes the packed word (quad key << id bits | sample id) of every visible sample,
+//       the chunk's histogram over kFine equal key ranges of the (cam, level) bucket as an exclusive prefix, and
+//       adds the histogram to the bucket's global one (integer atomics).  The only pass that touches every location.
+//   dfa_band_sort_kernel    per (b, cam, level, BAND): the bucket's key space is cut into bands of roughly EQUAL
+//       SAMPLE COUNT from the global histogram (every band CTA derives the same cuts; a band's records start at the
+//       prefix of the counts before it -- no cursor, no atomics).  The CTA picks the words of its key range out of
+//       the bucket's list (ordered: chunk order, then order inside the chunk), radix-sorts them by key in shared
+//       memory (stable LSD, ballot ranks), and emits 16-byte records {sample, anchor, lh, lw} + the
+//       record's G weights in sorted order plus its slice of the bucket's segment table seg[key] = first record with
+//       key' >= key.  The order INSIDE a key segment is the stable sample order, which is all the summation order
+//       depends on.  (Bands used to be equal ranges of quad ROWS: on a stage-2 layer one band of 24 held 11 700 of a
+//       camera's 14 400 samples on the coarsest level and ran 55 us while the average band CTA ran 17.)
 //   dfa_row_classify_kernel one thread per feature row: 4 segment lookups (row (y,x) is corner 1/2/3/4 of
 //       the quads keyed (y,x), (y,x-1), (y-1,x), (y-1,x-1)); touched rows are appended (warp-aggregated
 //       integer atomics) to work lists together with their segment bounds: rows with <= kTinyRow
@@ -35,9 +38,10 @@ constexpr int kVisChunk = 1024;          // samples per compaction chunk
 constexpr int kVisThreads = 256;
 constexpr int kRadixBits = 8;
 constexpr int kRadix = 1 << kRadixBits;
-constexpr int kMaxBands = 32;
-constexpr int kScanUnroll = 8;           // independent loads in flight per lane in the band kernel's scans
-constexpr int kSegScale = 8;             // ints of segment table per feature row (upper bound, see seg_offset)
+constexpr int kMaxBands = 32;            // band CTAs launched per (cam, level) bucket; a bucket uses as many as its samples need
+constexpr int kFine = 128;               // equal key ranges per bucket the histograms count (band cuts fall between them)
+constexpr int kCum = kFine + 4;          // ints per (chunk, level) prefix row: kFine + 1 used, padded to 16 bytes
+constexpr int kSegScale = 5;             // ints of segment table per feature row (upper bound, see seg_offset)
 constexpr int kClassifyThreads = 256;    // rows classified per CTA (one thread each)
 constexpr int kReduceCtas = 148 * 2;     // persistent CTAs (8 warps, 2 per SM; 4 per SM for the light variant) of the reduce kernel
 constexpr int kTinyRow = 8;              // contributions up to which a row is summed by a quarter warp
@@ -66,14 +70,15 @@ struct GfeatParams {
     int A_total;       // rows per batch element of the packed grad_out
     const float* grad_out;   // [bs, A_total, C]
     void* g_feat;
-    int* vis_id;       // [bs][cams][n_ids]    compacted visible sample ids, chunk c at [c*kVisChunk, ...)
-    float2* vis_xy;    // [bs][cams][n_ids]    their locations
-    int* vis_cnt;      // [bs][cams][n_chunks] visible samples per chunk
-    int* band_cnt;     // [bs][cams][n_chunks][L][kMaxBands] of them, per level, the ones whose quad row falls into each band
+    unsigned long long* vis_key;  // [bs][cams*L][n_ids] slots of 8 bytes: packed words (key << id bits | id) of the visible
+                                  // samples, chunk c at [c*kVisChunk, ...), grouped by fine bin inside the chunk; 32-bit
+                                  // words where key and id fit (list_is_wide)
+    int* chunk_cum;    // [bs][cams][n_chunks][L][kCum]  per chunk and level: samples whose fine bin is < f, f = 0..kFine
+    int* ghist;        // [bs][cams*L][kFine]  samples per fine bin of the bucket (zeroed before the compaction kernel)
     int4* rec;         // [bs][cams*L][n_ids]  sorted records {sample id, packed anchor row, lh, lw}
     float* recw;       // [bs][cams*L][n_ids][G] the G weights of each record's (sample, cam, level), in record order
-    int* seg;          // [bs][seg_stride]     segment tables (absolute positions inside the bucket's rec[])
-    int* cursor;       // [bs][cams*L]         records allocated so far in each bucket
+    int* seg;          // [bs][seg_stride]     segment tables: seg[key] = first record of the bucket with key' >= key
+    int* cursor;       // [bs][cams*L]         records of each bucket (written by the bucket's band 0)
     unsigned long long* sortbuf;  // [bs][cams*L][2][n_ids] global ping-pong (bands that exceed shared memory)
     int4* part_list;   // [bs*num_feat + partial_cap][4]  work-list entries (kEntryInts ints), one per part item
     int4* tiny_list;   // [bs*num_feat][4]                work-list entries, one per tiny row (tiny_ok only)
@@ -84,7 +89,8 @@ struct GfeatParams {
     Dims d;
     int seg_stride;    // ints per batch element in seg
     int n_chunks;
-    int NB;            // requested bands per bucket (<= kMaxBands)
+    int NB;            // band CTAs launched per bucket (<= kMaxBands)
+    int band_target;   // samples per band the cuts aim for
     int accumulate;    // add to the rows already in g_feat instead of overwriting them (shared buffer across calls)
     int tiny_max;      // rows with at most this many contributions go to the quarter-warp path (<= kTinyRow)
     int tiny_ok;       // shape supported by the quarter-warp kernel (C % 32 == 0, C <= 256, (C/G) % 32 == 0)
@@ -100,26 +106,37 @@ __device__ __forceinline__ int call_of_id(const GfeatParams& p, int sid) {
 }
 
 __host__ __device__ inline int bits_for(unsigned v) {   // number of bits to represent values < v
+#ifdef __CUDA_ARCH__
+    return (v <= 1u) ? 0 : 32 - __clz(v - 1u);
+#else
     int b = 0;
     while ((1ull << b) < (unsigned long long)v) ++b;
     return b;
+#endif
 }
 
-// Band geometry of a (cam, level) bucket of h x w pixels.  Quads are keyed in PADDED coordinates
-// (h_low+1, w_low+1) in [0,h] x [0,w]; band j owns padded quad rows [j*RB, (j+1)*RB).
-struct Bands {
-    int nb, RB, row_keys, tab;   // bands, quad rows per band, keys per quad row (w+1), ints per band table
+// Key space of a (cam, level) bucket of h x w pixels.  Quads are keyed in PADDED coordinates (h_low+1, w_low+1) in
+// [0,h] x [0,w], row-major key = row * (w+1) + column; fine bin f owns the keys [f*KF, (f+1)*KF).
+struct KeySpace {
+    int keys, row_keys, KF;      // (h+1)*(w+1), keys per quad row (w+1), keys per fine bin
 };
-__device__ __forceinline__ Bands band_geometry(int h, int w, int NB) {
-    Bands g;
-    g.nb = min(NB, h + 1);
-    g.RB = (h + 1 + g.nb - 1) / g.nb;
+__device__ __forceinline__ KeySpace key_space(int h, int w) {
+    KeySpace g;
     g.row_keys = w + 1;
-    g.tab = g.RB * g.row_keys + 1;       // + sentinel
+    g.keys = (h + 1) * g.row_keys;
+    g.KF = (g.keys + kFine - 1) / kFine;
     return g;
 }
-// Segment tables of bucket `cl` start at kSegScale * start[cl]:  nb*tab <= (2h+1)(w+1) + h + 1 <= 8*h*w,
-// so buckets whose row ranges are disjoint never overlap, whatever their order.
+// the key of a sample at a level: the same FMA + floor as quad_setup()
+__device__ __forceinline__ int quad_key(float x, float y, int h, int w) {
+    const int qr = __float2int_rd(__fmaf_rn(y, (float)h, -0.5f)) + 1;
+    const int qc = __float2int_rd(__fmaf_rn(x, (float)w, -0.5f)) + 1;
+    return qr * (w + 1) + qc;
+}
+// words of the bucket's list are 64-bit when (key, sample id) does not fit 32 bits (both kernels evaluate this)
+__device__ __forceinline__ bool list_is_wide(int keys, int id_bits) { return bits_for((unsigned)keys) + id_bits > 32; }
+// The segment table of bucket `cl` (keys + 1 entries) starts at kSegScale * start[cl]: (h+1)(w+1) + 1 <= 5*h*w for
+// every h, w >= 1, so buckets whose row ranges are disjoint never overlap, whatever their order.
 __device__ __forceinline__ size_t seg_offset(int start) { return (size_t)kSegScale * (size_t)start; }
 
 // ------------------------------------------------------------------------------------------ zero fill
@@ -136,9 +153,23 @@ __global__ void __launch_bounds__(256) dfa_zero_kernel(uint4* __restrict__ dst, 
     for (; i < n16; i += stride) dst[i] = z;
 }
 
+// lanes of the warp that hold the same `db`-bit digit (inactive lanes pass a digit nobody else has: bit `db` set).
+// One ballot per digit bit; __match_any_sync costs a multiple of this when the warp holds many distinct digits.
+__device__ __forceinline__ unsigned digit_peers(unsigned dgt, int db) {
+    unsigned peers = 0xffffffffu;
+    for (int bit = 0; bit <= db; ++bit) {
+        const unsigned vote = __ballot_sync(0xffffffffu, (dgt >> bit) & 1u);
+        peers &= ((dgt >> bit) & 1u) ? vote : ~vote;
+    }
+    return peers;
+}
+
 // ------------------------------------------------------------------------------------------ compaction
-// grid (n_chunks, cams, bs), block kVisThreads.  Warp w of chunk c owns samples
-// [c*kVisChunk + w*128, +128): ordered inside the chunk, chunks are concatenated by the consumers.
+// grid (n_chunks, cams, bs), block kVisThreads.  Per level the visible samples of the chunk
+// are written to the bucket's list GROUPED BY FINE BIN (stable: warp order, then order inside the warp -- the sample
+// order), so that a band CTA finds the words of its key range as one contiguous run per chunk and never looks at the
+// others (walking the whole list in every band CTA was the largest phase of the sort kernel: ~20 instructions per
+// word, bands x words times).
 __global__ void __launch_bounds__(kVisThreads) dfa_vis_compact_kernel(const GfeatParams p) {
     constexpr int kWarps = kVisThreads / 32;
     constexpr int kPerWarp = kVisChunk / kWarps;     // 128
@@ -149,69 +180,111 @@ __global__ void __launch_bounds__(kVisThreads) dfa_vis_compact_kernel(const Gfea
     const int kc = call_of_id(p, c * kVisChunk);          // a chunk belongs to exactly one call
     const GfeatCall& gc = p.calls[kc];
     const int AP = gc.A * gc.P;                           // samples of that call (per batch element)
-    __shared__ int s_wcnt[kWarps];
-    __shared__ int s_bc[kMaxCamLevels * kMaxBands];     // [level][band] counts of this chunk
+    __shared__ __align__(16) int s_wh[kWarps * kFine];    // per warp and fine bin: samples, then first slot inside the bin
+    __shared__ __align__(16) int s_cum[kFine];            // exclusive prefix over the bins of the level at hand
 
-    if (c == 0 && cam == 0) {
-        for (int i = tid; i < d.cams * d.L; i += kVisThreads) p.cursor[(size_t)b_idx * d.cams * d.L + i] = 0;
-        if (b_idx == 0 && tid < 8) p.counters[tid] = 0;
-    }
-    for (int i = tid; i < d.L * kMaxBands; i += kVisThreads) s_bc[i] = 0;
+    if (c == 0 && cam == 0 && b_idx == 0 && tid < 8) p.counters[tid] = 0;
     const float2* loc2 = reinterpret_cast<const float2*>(gc.loc) + (size_t)b_idx * AP * d.cams + cam;
     const int s_base = c * kVisChunk + warp * kPerWarp;   // group sample id
     const int s_local0 = s_base - gc.id_begin;            // sample index inside the call
     float2 xy[kIter];
-    unsigned bal[kIter];
-    int cnt = 0;
+    unsigned vis = 0;                                     // bit `it`: this lane's sample of iteration `it` is visible
+    bool any = false;
 #pragma unroll
     for (int it = 0; it < kIter; ++it) {
         const int s = s_local0 + it * 32 + lane;
         xy[it] = make_float2(-1.f, -1.f);
         if (s < AP) xy[it] = __ldg(loc2 + (size_t)s * d.cams);
-        bal[it] = __ballot_sync(0xffffffffu, loc_valid(xy[it].x, xy[it].y));
-        cnt += __popc(bal[it]);
+        if (loc_valid(xy[it].x, xy[it].y)) vis |= 1u << it;
     }
-    if (lane == 0) s_wcnt[warp] = cnt;
-    __syncthreads();
-    // per level: which band of quad rows each visible sample falls into (the band kernel's work split), counted
-    // here so that the band kernel needs a single pass over the compacted list
+    any = __syncthreads_or(vis != 0);
+    const int id_bits = bits_for((unsigned)p.n_ids);
+    int* cum = p.chunk_cum + (((size_t)b_idx * d.cams + cam) * p.n_chunks + c) * d.L * kCum;
+    if (!any) {      // nothing of this chunk is visible to the camera (most chunks of the side and rear cameras)
+        for (int i = tid; i < d.L * kCum; i += kVisThreads) cum[i] = 0;
+        return;
+    }
+    const unsigned lt = (1u << lane) - 1u;
     for (int l = 0; l < d.L; ++l) {
-        const int h = __ldg(p.shapes + (cam * d.L + l) * 2), w = __ldg(p.shapes + (cam * d.L + l) * 2 + 1);
-        const Bands g = band_geometry(h, w, p.NB);
+        const int cl = cam * d.L + l;
+        const int h = __ldg(p.shapes + cl * 2), w = __ldg(p.shapes + cl * 2 + 1);
+        const KeySpace g = key_space(h, w);
+        for (int i = tid; i < kWarps * kFine; i += kVisThreads) s_wh[i] = 0;
+        __syncthreads();
+        // rank of every visible sample among the samples of its warp that fall into the same bin
+        int key[kIter], rank[kIter], fbin[kIter];
+        int* my = s_wh + warp * kFine;
 #pragma unroll
         for (int it = 0; it < kIter; ++it) {
-            if ((bal[it] >> lane) & 1u) {
-                const int qr = __float2int_rd(__fmaf_rn(xy[it].y, (float)h, -0.5f)) + 1;   // quad_setup()'s h_low + 1
-                atomicAdd(&s_bc[l * kMaxBands + qr / g.RB], 1);
+            const bool v = (vis >> it) & 1u;
+            key[it] = v ? quad_key(xy[it].x, xy[it].y, h, w) : 0;
+            const unsigned bin = v ? (unsigned)(key[it] / g.KF) : (unsigned)kFine;
+            fbin[it] = (int)bin;
+            const unsigned peers = digit_peers(bin, 7);
+            rank[it] = v ? my[bin] + __popc(peers & lt) : 0;
+            __syncwarp();
+            if (v && lane == __ffs(peers) - 1) my[bin] += __popc(peers);
+            __syncwarp();
+        }
+        __syncthreads();
+        int count = 0;
+        if (tid < kFine) {     // bin totals; s_wh becomes the first slot of (warp, bin) inside the bin
+#pragma unroll
+            for (int wq = 0; wq < kWarps; ++wq) {
+                const int n = s_wh[wq * kFine + tid];
+                s_wh[wq * kFine + tid] = count;
+                count += n;
+            }
+            s_cum[tid] = count;
+        }
+        __syncthreads();
+        if (warp == 0) {       // exclusive prefix over the bins (4 per lane), the chunk's prefix row, the bucket's histogram
+            const int4 v = *reinterpret_cast<const int4*>(s_cum + lane * 4);
+            const int mine = v.x + v.y + v.z + v.w;
+            int inc = mine;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += t;
+            }
+            const int ex = inc - mine;
+            const int4 e4 = make_int4(ex, ex + v.x, ex + v.x + v.y, ex + v.x + v.y + v.z);
+            *reinterpret_cast<int4*>(s_cum + lane * 4) = e4;
+            *reinterpret_cast<int4*>(cum + l * kCum + lane * 4) = e4;
+            if (lane == 31) cum[l * kCum + kFine] = inc;
+            if (mine > 0) {
+                int* gh = p.ghist + ((size_t)b_idx * d.cams * d.L + cl) * kFine + lane * 4;
+                if (v.x) atomicAdd(gh + 0, v.x);
+                if (v.y) atomicAdd(gh + 1, v.y);
+                if (v.z) atomicAdd(gh + 2, v.z);
+                if (v.w) atomicAdd(gh + 3, v.w);
             }
         }
-    }
-    int pos = 0, total = 0;
+        __syncthreads();
+        const bool wide = list_is_wide(g.keys, id_bits);
+        unsigned long long* slots = p.vis_key + ((size_t)b_idx * d.cams * d.L + cl) * p.n_ids;
+        unsigned long long* l64 = slots + (size_t)c * kVisChunk;
+        unsigned* l32 = reinterpret_cast<unsigned*>(slots) + (size_t)c * kVisChunk;
+        // rank[] was taken before s_wh turned into first slots: slot = bin start + the warp's first slot in the bin + rank
 #pragma unroll
-    for (int w = 0; w < kWarps; ++w) {
-        const int n = s_wcnt[w];
-        if (w < warp) pos += n;
-        total += n;
-    }
-    const size_t list = ((size_t)b_idx * d.cams + cam) * p.n_ids + (size_t)c * kVisChunk;
-#pragma unroll
-    for (int it = 0; it < kIter; ++it) {
-        if ((bal[it] >> lane) & 1u) {
-            const int at = pos + __popc(bal[it] & ((1u << lane) - 1u));
-            p.vis_id[list + at] = s_base + it * 32 + lane;
-            p.vis_xy[list + at] = xy[it];
+        for (int it = 0; it < kIter; ++it) {
+            if ((vis >> it) & 1u) {
+                const int bin = fbin[it];
+                const int at = s_cum[bin] + my[bin] + rank[it];
+                const unsigned id = (unsigned)(s_base + it * 32 + lane);
+                if (wide) l64[at] = ((unsigned long long)key[it] << id_bits) | id;
+                else l32[at] = ((unsigned)key[it] << id_bits) | id;
+            }
         }
-        pos += __popc(bal[it]);
+        __syncthreads();       // s_wh / s_cum are rewritten by the next level
     }
-    if (tid == 0) p.vis_cnt[((size_t)b_idx * d.cams + cam) * p.n_chunks + c] = total;
-    __syncthreads();
-    int* bc = p.band_cnt + (((size_t)b_idx * d.cams + cam) * p.n_chunks + c) * d.L * kMaxBands;
-    for (int i = tid; i < d.L * kMaxBands; i += kVisThreads) bc[i] = s_bc[i];
 }
 
 // ------------------------------------------------------------------------------------------ band sort
-// Stable LSD radix sort of n packed words on bits [lo_bit, lo_bit + nbits) by one CTA of kSortThreads.
+// Stable LSD radix sort of n packed words on bits [lo_bit, lo_bit + nbits) by one CTA of kT threads.
 // a/b: ping-pong arrays (shared or global).  Returns the array holding the result.
+// The nbits are split evenly over ceil(nbits / 8) passes (10 bits -> 5 + 5, not 8 + 2): what a pass costs besides the
+// two walks over the words is proportional to its digit count (per-warp histograms: zero, column scan, base add).
 template <typename W, int kT>
 __device__ W* block_radix_sort(W* a, W* b, int n, int lo_bit, int nbits, unsigned* hist /*[kSortWarps][kRadix]*/,
                                unsigned* tot /*[kRadix + 32]*/) {
@@ -220,58 +293,76 @@ __device__ W* block_radix_sort(W* a, W* b, int n, int lo_bit, int nbits, unsigne
     int chunk = (n + kSortWarps - 1) / kSortWarps;
     chunk = (chunk + 31) & ~31;
     const int beg = min(n, warp * chunk), end = min(n, beg + chunk);
-    for (int shift = lo_bit; shift < lo_bit + nbits; shift += kRadixBits) {
-        unsigned* my = hist + warp * kRadix;
-        for (int i = lane; i < kRadix; i += 32) my[i] = 0;
+    const int passes = (nbits + kRadixBits - 1) / kRadixBits;
+    int shift = lo_bit;
+    for (int pass = 0; pass < passes; ++pass) {
+        const int left = lo_bit + nbits - shift;
+        const int db = (left + (passes - pass) - 1) / (passes - pass);     // digit bits of this pass (<= kRadixBits)
+        const int R = 1 << db;
+        const unsigned dmask = (unsigned)R - 1u;
+        unsigned* my = hist + warp * R;
+        for (int i = lane; i < R; i += 32) my[i] = 0;
         __syncwarp();
         for (int i0 = beg; i0 < end; i0 += 32) {
             const int i = i0 + lane;
             const bool has = i < end;
-            const unsigned dgt = has ? (unsigned)((a[i] >> shift) & (kRadix - 1)) : kRadix;
-            const unsigned peers = __match_any_sync(0xffffffffu, dgt);
+            const unsigned dgt = has ? ((unsigned)(a[i] >> shift) & dmask) : (unsigned)R;
+            const unsigned peers = digit_peers(dgt, db);
             if (has && lane == __ffs(peers) - 1) my[dgt] += __popc(peers);
             __syncwarp();
         }
         __syncthreads();
-        if (tid < kRadix) {
+        if (tid < R) {                      // digit totals over the warps
             unsigned run = 0;
 #pragma unroll
-            for (int w = 0; w < kSortWarps; ++w) {
-                const unsigned c = hist[w * kRadix + tid];
-                hist[w * kRadix + tid] = run;
-                run += c;
-            }
+            for (int w = 0; w < kSortWarps; ++w) run += hist[w * R + tid];
             tot[tid] = run;
         }
         __syncthreads();
-        if (tid < kRadix) {   // exclusive scan of the 256 digit totals: warp scan + 8 warp carries
-            const unsigned mine = tot[tid];
+        if (warp == 0) {                    // exclusive scan of the R totals: lane owns R/32 consecutive digits
+            const int per = (R + 31) >> 5;
+            unsigned mine = 0;
+            for (int j = 0; j < per; ++j) {
+                const int dg = lane * per + j;
+                if (dg < R) mine += tot[dg];
+            }
             unsigned inc = mine;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
                 const unsigned t = __shfl_up_sync(0xffffffffu, inc, o);
                 if (lane >= o) inc += t;
             }
-            if (lane == 31) tot[kRadix + warp] = inc;
-            __syncwarp();
-            asm volatile("bar.sync 1, 256;");              // only the first 8 warps take part
-            unsigned base = 0;
-            for (int ww = 0; ww < warp; ++ww) base += tot[kRadix + ww];
-            base += inc - mine;
+            unsigned run = inc - mine;
+            for (int j = 0; j < per; ++j) {
+                const int dg = lane * per + j;
+                if (dg < R) {
+                    const unsigned c = tot[dg];
+                    tot[dg] = run;
+                    run += c;
+                }
+            }
+        }
+        __syncthreads();
+        if (tid < R) {                      // first slot of (warp, digit): digit base + the warps before
+            unsigned run = tot[tid];
 #pragma unroll
-            for (int w = 0; w < kSortWarps; ++w) hist[w * kRadix + tid] += base;
+            for (int w = 0; w < kSortWarps; ++w) {
+                const unsigned c = hist[w * R + tid];
+                hist[w * R + tid] = run;
+                run += c;
+            }
         }
         __syncthreads();
         for (int i0 = beg; i0 < end; i0 += 32) {
             const int i = i0 + lane;
             const bool has = i < end;
             W word = 0;
-            unsigned dgt = kRadix;
+            unsigned dgt = (unsigned)R;
             if (has) {
                 word = a[i];
-                dgt = (unsigned)((word >> shift) & (kRadix - 1));
+                dgt = (unsigned)(word >> shift) & dmask;
             }
-            const unsigned peers = __match_any_sync(0xffffffffu, dgt);
+            const unsigned peers = digit_peers(dgt, db);
             if (has) {
                 const unsigned pos = my[dgt] + __popc(peers & ((1u << lane) - 1u));
                 b[pos] = word;
@@ -282,119 +373,162 @@ __device__ W* block_radix_sort(W* a, W* b, int n, int lo_bit, int nbits, unsigne
         }
         __syncthreads();
         W* t = a; a = b; b = t;
+        shift += db;
     }
     return a;
 }
 
 struct BandCtx {
-    int b_idx, cam, cl, h, w, q0, q1, K, n, base, vb, kb;
-    const int* s_coff;    // per chunk: offset of its first in-band sample inside the band's list
+    int b_idx, cam, cl, h, w, q0, q1, K, n, base, vb, kb, keys;     // [q0, q1): the band's key range
+    const int* s_coff;    // per chunk: offset of its first in-band sample inside the band's list ([n_chunks] = n)
+    const int* s_from;    // per chunk: where the band's run starts inside the chunk's words
+    int tr;               // trace slot of this CTA (development builds)
 };
 
-// compaction (chunk order, then order inside the chunk) + sort + record/segment emission of one band
-template <typename W, int kT>
+// gather (chunk order, then order inside the chunk) + sort + record/segment emission of one band.
+// LW: word type of the bucket's list, W: word type of the band's sort (local key << id bits | id)
+template <typename W, typename LW, int kT>
 __device__ void band_sort_body(const GfeatParams& p, const BandCtx& bc, W* a, W* b, unsigned* hist, unsigned* tot,
-                               int* seg_band) {
+                               int* seg_bucket) {
     constexpr int kSortThreads = kT, kSortWarps = kT / 32;
     const Dims d = p.d;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int AP = p.n_ids;
-    const size_t cam_list = ((size_t)bc.b_idx * d.cams + bc.cam) * AP;
-    const int* cnts = p.vis_cnt + ((size_t)bc.b_idx * d.cams + bc.cam) * p.n_chunks;
+    const LW* list = reinterpret_cast<const LW*>(p.vis_key + ((size_t)bc.b_idx * d.cams * d.L + bc.cl) * AP);
 
-    for (int c = warp; c < p.n_chunks; c += kSortWarps) {
-        const int cnt = __ldg(cnts + c);
-        const int* ids = p.vis_id + cam_list + (size_t)c * kVisChunk;
-        const float2* xys = p.vis_xy + cam_list + (size_t)c * kVisChunk;
-        int pos = bc.s_coff[c];
-        for (int i0 = 0; i0 < cnt; i0 += 32 * kScanUnroll) {
-            float2 xy[kScanUnroll];
-            int id[kScanUnroll];
+    // the band's words are one contiguous run per chunk (the compaction kernel groups a chunk's words by fine bin):
+    // warp w copies the runs of chunks w, w + kSortWarps, ..., four chunks' loads in flight at a time, and turns the
+    // bucket-wide key into the band's local one
+    {
+        const LW sub = (LW)bc.q0 << bc.vb;
+        for (int c0 = warp; c0 < p.n_chunks; c0 += 4 * kSortWarps) {
+            LW wd[4];
+            int cnt[4], dst[4];
 #pragma unroll
-            for (int u = 0; u < kScanUnroll; ++u) {
-                const int i = i0 + u * 32 + lane;
-                xy[u] = make_float2(-1.f, -1.f);
-                id[u] = 0;
-                if (i < cnt) {
-                    xy[u] = __ldg(xys + i);
-                    id[u] = __ldg(ids + i);
+            for (int u = 0; u < 4; ++u) {
+                const int c = c0 + u * kSortWarps;
+                cnt[u] = 0;
+                dst[u] = 0;
+                wd[u] = 0;
+                if (c < p.n_chunks) {
+                    dst[u] = bc.s_coff[c];
+                    cnt[u] = bc.s_coff[c + 1] - dst[u];
+                    if (lane < cnt[u]) wd[u] = __ldg(list + (size_t)c * kVisChunk + bc.s_from[c] + lane);
                 }
             }
 #pragma unroll
-            for (int u = 0; u < kScanUnroll; ++u) {
-                if (i0 + u * 32 >= cnt) break;   // warp-uniform
-                // every band CTA of the bucket walks the camera's whole list: test the band with the row index alone
-                // (the same FMA + floor as quad_setup()), the column only for the 1/NB of the entries that stay
-                const int qr = __float2int_rd(__fmaf_rn(xy[u].y, (float)bc.h, -0.5f)) + 1;
-                const bool in = (i0 + u * 32 + lane < cnt) && qr >= bc.q0 && qr < bc.q1;
-                const unsigned bal = __ballot_sync(0xffffffffu, in);
-                if (in) {
-                    const int qc = __float2int_rd(__fmaf_rn(xy[u].x, (float)bc.w, -0.5f)) + 1;
-                    const unsigned key = (unsigned)((qr - bc.q0) * (bc.w + 1) + qc);
-                    a[pos + __popc(bal & ((1u << lane) - 1u))] = ((W)key << bc.vb) | (W)id[u];
+            for (int u = 0; u < 4; ++u) {
+                if (lane < cnt[u]) a[dst[u] + lane] = (W)(wd[u] - sub);
+                if (cnt[u] > 32) {     // warp-uniform; a chunk rarely holds more than 32 words of one band
+                    const int c = c0 + u * kSortWarps;
+                    const LW* src = list + (size_t)c * kVisChunk + bc.s_from[c];
+                    for (int i = 32 + lane; i < cnt[u]; i += 32) a[dst[u] + i] = (W)(__ldg(src + i) - sub);
                 }
-                pos += __popc(bal);
             }
         }
     }
     __syncthreads();
+    DFA_TRACE(bc.tr, 4);
 
     W* sorted = block_radix_sort<W, kT>(a, b, bc.n, bc.vb, bc.kb, hist, tot);
+    DFA_TRACE(bc.tr, 5);
 
     // sorted records: everything the reduce needs per contribution, so it never re-derives the quad
     int4* rec = p.rec + ((size_t)bc.b_idx * d.cams * d.L + bc.cl) * AP + bc.base;
     float* recw = p.recw + (((size_t)bc.b_idx * d.cams * d.L + bc.cl) * AP + bc.base) * d.G;
     const int lvl = bc.cl - bc.cam * d.L;
     const W vmask = ((W)1 << bc.vb) - 1;
-    for (int i0 = 0; i0 < bc.n; i0 += kSortThreads * 2) {
-        int sid[2], arow[2];
-        float2 xy[2];
-        const float* wsrc[2];
+    constexpr int kEmit = 4;      // records per thread whose loads are in flight together
+    for (int i0 = 0; i0 < bc.n; i0 += kSortThreads * kEmit) {
+        int sid[kEmit], arow[kEmit];
+        float2 xy[kEmit];
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
+        for (int u = 0; u < kEmit; ++u) {
             const int i = i0 + u * kSortThreads + tid;
             sid[u] = (i < bc.n) ? (int)(sorted[i] & vmask) : p.calls[0].id_begin;
             const GfeatCall& gc = p.calls[call_of_id(p, sid[u])];
             const int s_local = sid[u] - gc.id_begin;
             const size_t s_abs = (size_t)bc.b_idx * gc.A * gc.P + s_local;      // sample inside the call's tensors
             xy[u] = __ldg(reinterpret_cast<const float2*>(gc.loc) + s_abs * d.cams + bc.cam);
-            wsrc[u] = gc.weights + ((s_abs * d.cams + bc.cam) * d.L + lvl) * d.G;
             arow[u] = gc.anchor_begin + s_local / gc.P;
         }
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
+        for (int u = 0; u < kEmit; ++u) {
             const int i = i0 + u * kSortThreads + tid;
             if (i < bc.n) {
                 const Quad q = quad_setup(xy[u].x, xy[u].y, bc.h, bc.w);
                 rec[i] = make_int4(sid[u], arow[u], __float_as_int(q.lh), __float_as_int(q.lw));
-                // the record's G weights travel with it, so the reduce reads them sequentially and never has to
-                // find the call a contribution came from
-                float* wd = recw + (size_t)i * d.G;
-                if ((d.G & 3) == 0) {
-                    for (int g = 0; g < d.G; g += 4)
-                        *reinterpret_cast<float4*>(wd + g) = __ldg(reinterpret_cast<const float4*>(wsrc[u] + g));
-                } else {
-                    for (int g = 0; g < d.G; ++g) wd[g] = __ldg(wsrc[u] + g);
-                }
             }
         }
     }
-
-    // seg[k] = first record (absolute position in the bucket) whose key >= k, k = 0..K (K = sentinel):
-    // a lower-bound search in the sorted words per key -- no fill / mark / scan phases, no barriers
-    for (int k = tid; k <= bc.K; k += kSortThreads) {
-        int lo = 0, hi = bc.n;
-        while (lo < hi) {
-            const int mid = (lo + hi) >> 1;
-            if ((int)(sorted[mid] >> bc.vb) < k) lo = mid + 1; else hi = mid;
+    // the record's G weights travel with it, so the reduce reads them sequentially and never has to find the call a
+    // contribution came from: one thread per 16 bytes, stores in record order (coalesced)
+    if ((d.G & 3) == 0) {
+        const int q_per = d.G >> 2, total = bc.n * q_per;
+        float4* dst = reinterpret_cast<float4*>(recw);
+        for (int e0 = 0; e0 < total; e0 += kSortThreads * kEmit) {
+            float4 v[kEmit];
+#pragma unroll
+            for (int u = 0; u < kEmit; ++u) {
+                const int e = min(e0 + u * kSortThreads + tid, total - 1);
+                const int i = e / q_per, part = e - i * q_per;
+                const int sid = (int)(sorted[i] & vmask);
+                const GfeatCall& gc = p.calls[call_of_id(p, sid)];
+                const size_t s_abs = (size_t)bc.b_idx * gc.A * gc.P + (sid - gc.id_begin);
+                v[u] = __ldg(reinterpret_cast<const float4*>(gc.weights + ((s_abs * d.cams + bc.cam) * d.L + lvl) * d.G) + part);
+            }
+#pragma unroll
+            for (int u = 0; u < kEmit; ++u) {
+                const int e = e0 + u * kSortThreads + tid;
+                if (e < total) dst[e] = v[u];
+            }
         }
-        seg_band[k] = bc.base + lo;
+    } else {
+        for (int e = tid; e < bc.n * d.G; e += kSortThreads) {
+            const int i = e / d.G, g = e - i * d.G;
+            const int sid = (int)(sorted[i] & vmask);
+            const GfeatCall& gc = p.calls[call_of_id(p, sid)];
+            const size_t s_abs = (size_t)bc.b_idx * gc.A * gc.P + (sid - gc.id_begin);
+            recw[e] = __ldg(gc.weights + ((s_abs * d.cams + bc.cam) * d.L + lvl) * d.G + g);
+        }
     }
+    DFA_TRACE(bc.tr, 6);
+
+    // seg[q0 + k] = first record (position inside the bucket) whose key >= q0 + k, k = 0..K-1: a lower-bound search in
+    // the sorted words per key -- no fill / mark / scan phases, no barriers.  The band that owns the bucket's last key
+    // also writes the end marker seg[keys].
+    // record i is the first of key k_i: the keys (k_{i-1}, k_i] start at i.  Keys up to the first record's start at 0,
+    // keys after the last record's at n (the band that owns the bucket's last key also writes the end marker seg[keys]).
+    const int k_end = bc.K + ((bc.q1 == bc.keys) ? 1 : 0);
+    const int k_first = (int)(sorted[0] >> bc.vb), k_last = (int)(sorted[bc.n - 1] >> bc.vb);   // n > 0 (checked by the kernel)
+    int* seg_band = seg_bucket + bc.q0;
+    for (int k = tid; k <= k_first; k += kSortThreads) seg_band[k] = bc.base;
+    for (int k = k_last + 1 + tid; k < k_end; k += kSortThreads) seg_band[k] = bc.base + bc.n;
+    for (int i0 = warp * 32; i0 < bc.n; i0 += kSortThreads) {
+        const int i = i0 + lane;
+        int key = 0, gap = 0;
+        if (i > 0 && i < bc.n) {
+            key = (int)(sorted[i] >> bc.vb);
+            gap = key - (int)(sorted[i - 1] >> bc.vb);
+        }
+        // short gaps (the usual case: 0 = same key, 1 = next key) by the record's own thread, long ones by the warp
+        for (int t = 0; t < min(gap, 4); ++t) seg_band[key - t] = bc.base + i;
+        unsigned big = __ballot_sync(0xffffffffu, gap > 4);
+        while (big) {
+            const int src = __ffs(big) - 1;
+            big &= big - 1;
+            const int kk = __shfl_sync(0xffffffffu, key, src), gg = __shfl_sync(0xffffffffu, gap, src);
+            for (int t = 4 + lane; t < gg; t += 32) seg_band[kk - t] = bc.base + i0 + src;
+        }
+    }
+    DFA_TRACE(bc.tr, 7);
+    DFA_TRACE_V(bc.tr, 8, bc.n);
+    DFA_TRACE_END(bc.tr, 9);
 }
 
-// dynamic smem: hist[warps*kRadix] + tot[kRadix+32] + misc[16] + coff[n_chunks] + 2*cap words
+// dynamic smem: hist[warps*kRadix] + tot[kRadix+32] + misc[16] + fine[kFine+4] + coff[n_chunks] + from[n_chunks] + 2*cap words
 inline size_t band_sort_smem_bytes(int n_chunks, int threads, int cap) {
-    return (size_t)((threads / 32) * kRadix + kRadix + 32 + 16 + ((n_chunks + 3) & ~3)) * 4 + (size_t)cap * 2 * 4;
+    return (size_t)((threads / 32) * kRadix + kRadix + 32 + 16 + (kFine + 4) + 2 * ((n_chunks + 4) & ~3)) * 4 + (size_t)cap * 2 * 4;
 }
 
 // grid (NB, cams*L, bs), block kT threads (>= 256: the digit scan uses the first 8 warps); kCap packed words per
@@ -407,43 +541,101 @@ __global__ void __launch_bounds__(kT, (kT >= 512) ? 2 : 4) dfa_band_sort_kernel(
     const int cam = cl / d.L;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int AP = p.n_ids;
-    const int h = __ldg(p.shapes + cl * 2), w = __ldg(p.shapes + cl * 2 + 1);
-    const Bands g = band_geometry(h, w, p.NB);
-    if (band >= g.nb) return;
     BandCtx bc;
-    bc.b_idx = b_idx; bc.cam = cam; bc.cl = cl; bc.h = h; bc.w = w;
-    bc.q0 = band * g.RB;
-    bc.q1 = min(h + 1, bc.q0 + g.RB);
-    if (bc.q0 >= bc.q1) return;        // no quad row maps to this band, nobody reads its table
-    bc.K = (bc.q1 - bc.q0) * g.row_keys;
-    bc.vb = bits_for((unsigned)AP);
-    bc.kb = bits_for((unsigned)bc.K);
+    bc.tr = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+    DFA_TRACE_BEGIN(bc.tr);
+    DFA_TRACE(bc.tr, 2);
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unsigned* hist = reinterpret_cast<unsigned*>(smem_raw);
     unsigned* tot = hist + kSortWarps * kRadix;
-    int* s_misc = reinterpret_cast<int*>(tot + kRadix + 32);     // [0] n  [1] base
-    int* s_coff = s_misc + 16;
-    unsigned char* data = reinterpret_cast<unsigned char*>(s_coff + ((p.n_chunks + 3) & ~3));
+    int* s_misc = reinterpret_cast<int*>(tot + kRadix + 32);     // [0] f0  [1] f1  [2] last bin with samples  [4..7] warp totals of the fine scan
+    int* s_fine = s_misc + 16;                                   // [kFine + 1] exclusive prefix of the bucket's histogram
+    int* s_coff = s_fine + kFine + 4;      // the two per-chunk arrays are (n_chunks + 4) & ~3 ints apart
+    int* s_from = s_coff + ((p.n_chunks + 4) & ~3);
+    unsigned char* data = reinterpret_cast<unsigned char*>(s_from + ((p.n_chunks + 4) & ~3));
 
-    // in-band samples per chunk, counted by the compaction kernel
+    // the bucket's histogram -> exclusive prefix E[0..kFine] (E[kFine] = samples of the bucket)
+    {
+        int mine = 0, inc = 0;
+        if (tid < kFine) mine = __ldg(p.ghist + ((size_t)b_idx * d.cams * d.L + cl) * kFine + tid);
+        // A bucket without samples (rear cameras of the planning query, every camera of the ego query) stays empty:
+        // cursor == 0 is what the row classification checks before it reads any segment table
+        if (!__syncthreads_or(mine > 0)) {
+            if (band == 0 && tid == 0) p.cursor[(size_t)b_idx * d.cams * d.L + cl] = 0;
+            return;
+        }
+        if (tid < kFine) {
+            inc = mine;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += t;
+            }
+            if (lane == 31) s_misc[4 + warp] = inc;
+        }
+        __syncthreads();
+        if (tid < kFine) {
+            int before = 0;
+#pragma unroll
+            for (int w = 0; w < kFine / 32; ++w)
+                if (w < warp) before += s_misc[4 + w];
+            s_fine[tid] = before + inc - mine;
+            if (tid == kFine - 1) s_fine[kFine] = before + inc;
+        }
+        __syncthreads();
+    }
+    const int N = s_fine[kFine];
+    if (band == 0 && tid == 0) p.cursor[(size_t)b_idx * d.cams * d.L + cl] = N;
+    // bands of ~band_target samples, cut between fine bins: band j starts at the first bin whose prefix reaches
+    // ceil(j*N/nb) -- every CTA of the bucket derives the same cuts
+    const int nb = max(1, min(p.NB, (N + p.band_target - 1) / p.band_target));
+    if (band >= nb) return;
+    {
+        const long long t0 = ((long long)band * N + nb - 1) / nb, t1 = ((long long)(band + 1) * N + nb - 1) / nb;
+        if (tid <= kFine) {
+            const int e = s_fine[tid], prev = (tid == 0) ? -1 : s_fine[tid - 1];
+            if (e >= t0 && prev < t0) s_misc[0] = tid;
+            if (e >= t1 && prev < t1) s_misc[1] = tid;
+        }
+        __syncthreads();
+    }
+    const int f0 = s_misc[0], f1 = (band == nb - 1) ? kFine : s_misc[1];
+    // last fine bin of the band that holds a sample: the sort only has to tell the keys up to there apart
+    if (tid == 0) s_misc[2] = f0;
+    __syncthreads();
+    if (tid >= f0 && tid < f1 && s_fine[tid + 1] > s_fine[tid]) atomicMax(&s_misc[2], tid);
+    __syncthreads();
+    const int h = __ldg(p.shapes + cl * 2), w = __ldg(p.shapes + cl * 2 + 1);
+    const KeySpace g = key_space(h, w);
+    bc.b_idx = b_idx; bc.cam = cam; bc.cl = cl; bc.h = h; bc.w = w; bc.keys = g.keys;
+    bc.q0 = min(g.keys, f0 * g.KF);
+    bc.q1 = min(g.keys, f1 * g.KF);
+    if (bc.q0 >= bc.q1) return;        // no key maps to this band (then it holds no sample either)
+    bc.K = bc.q1 - bc.q0;
+    bc.vb = bits_for((unsigned)AP);
+    bc.kb = bits_for((unsigned)min(bc.K, (s_misc[2] + 1 - f0) * g.KF));
+    bc.base = s_fine[f0];
+    bc.n = s_fine[f1] - s_fine[f0];
+    int* seg_bucket = p.seg + (size_t)b_idx * p.seg_stride + seg_offset(__ldg(p.starts + cl));
+    if (bc.n == 0) {                   // keys without samples (sky, road ahead of nothing): empty segments at `base`
+        for (int k = tid; k < bc.K + ((bc.q1 == bc.keys) ? 1 : 0); k += kSortThreads) seg_bucket[bc.q0 + k] = bc.base;
+        return;
+    }
+
+    // in-band samples per chunk (two prefix entries of the chunk's histogram), then their exclusive scan
     {
         const int l = cl - cam * d.L;
-        const int* bcnt = p.band_cnt + ((size_t)b_idx * d.cams + cam) * p.n_chunks * d.L * kMaxBands + l * kMaxBands + band;
-        for (int c = tid; c < p.n_chunks; c += kSortThreads) s_coff[c] = __ldg(bcnt + (size_t)c * d.L * kMaxBands);
-    }
-    if (warp == 1) {    // visible samples of the whole camera: nothing to do for any band when there are none
-        const int* cnts = p.vis_cnt + ((size_t)b_idx * d.cams + cam) * p.n_chunks;
-        int t = 0;
-        for (int c = lane; c < p.n_chunks; c += 32) t += __ldg(cnts + c);
-        t = __reduce_add_sync(0xffffffffu, t);
-        if (lane == 0) s_misc[2] = t;
+        const int* cum = p.chunk_cum + (((size_t)b_idx * d.cams + cam) * p.n_chunks * d.L + l) * kCum;
+        for (int c = tid; c < p.n_chunks; c += kSortThreads) {
+            const int* row = cum + (size_t)c * d.L * kCum;
+            const int from = __ldg(row + f0);
+            s_coff[c] = __ldg(row + f1) - from;
+            s_from[c] = from;
+        }
     }
     __syncthreads();
-    // A camera that sees no sample at all (rear cameras of the planning query, every camera of the ego query):
-    // its buckets stay empty (cursor == 0), which the row classification checks before it reads any segment table
-    if (s_misc[2] == 0) return;
-    if (warp == 0) {    // exclusive scan over the chunks
+    if (warp == 0) {    // exclusive scan of the in-band counts over the chunks
         int run = 0;
         for (int c0 = 0; c0 < p.n_chunks; c0 += 32) {
             const int c = c0 + lane;
@@ -457,34 +649,33 @@ __global__ void __launch_bounds__(kT, (kT >= 512) ? 2 : 4) dfa_band_sort_kernel(
             if (c < p.n_chunks) s_coff[c] = run + inc - m;
             run += __shfl_sync(0xffffffffu, inc, 31);
         }
-        if (lane == 0) {
-            s_misc[0] = run;
-            s_misc[1] = atomicAdd(p.cursor + (size_t)b_idx * d.cams * d.L + cl, run);
-        }
+        if (lane == 0) s_coff[p.n_chunks] = run;
     }
     __syncthreads();
-    bc.n = s_misc[0];
-    bc.base = s_misc[1];
     bc.s_coff = s_coff;
+    bc.s_from = s_from;
+    DFA_TRACE(bc.tr, 3);
 
-    int* seg_band = p.seg + (size_t)b_idx * p.seg_stride + seg_offset(__ldg(p.starts + cl)) + (size_t)band * g.tab;
     // bands that overflow shared memory sort in their slice [base, base+n) of the bucket's global buffers
     unsigned long long* gbuf = p.sortbuf + ((size_t)b_idx * d.cams * d.L + cl) * 2 * AP;
+    const bool wide_list = list_is_wide(g.keys, bc.vb);
     if (bc.vb + bc.kb <= 32) {
-        if (bc.n <= kBandCap) {
-            unsigned* a = reinterpret_cast<unsigned*>(data);
-            band_sort_body<unsigned, kT>(p, bc, a, a + kBandCap, hist, tot, seg_band);
-        } else {
-            unsigned* a = reinterpret_cast<unsigned*>(gbuf) + bc.base;
-            band_sort_body<unsigned, kT>(p, bc, a, a + AP, hist, tot, seg_band);
+        unsigned* a = reinterpret_cast<unsigned*>(data);
+        unsigned* b2 = a + kBandCap;
+        if (bc.n > kBandCap) {
+            a = reinterpret_cast<unsigned*>(gbuf) + bc.base;
+            b2 = a + AP;
         }
+        if (wide_list) band_sort_body<unsigned, unsigned long long, kT>(p, bc, a, b2, hist, tot, seg_bucket);
+        else band_sort_body<unsigned, unsigned, kT>(p, bc, a, b2, hist, tot, seg_bucket);
     } else {
-        if (bc.n <= kBandCap / 2) {
-            unsigned long long* a = reinterpret_cast<unsigned long long*>(data);
-            band_sort_body<unsigned long long, kT>(p, bc, a, a + kBandCap / 2, hist, tot, seg_band);
-        } else {
-            band_sort_body<unsigned long long, kT>(p, bc, gbuf + bc.base, gbuf + AP + bc.base, hist, tot, seg_band);
+        unsigned long long* a = reinterpret_cast<unsigned long long*>(data);
+        unsigned long long* b2 = a + kBandCap / 2;
+        if (bc.n > kBandCap / 2) {
+            a = gbuf + bc.base;
+            b2 = gbuf + AP + bc.base;
         }
+        band_sort_body<unsigned long long, unsigned long long, kT>(p, bc, a, b2, hist, tot, seg_bucket);
     }
 }
 
@@ -606,21 +797,20 @@ __device__ __forceinline__ void accumulate_row(const RowCtx<V, NCH>& cx, int c_l
     }
 }
 
-// row (y,x) of a bucket: the four quad-key segments that contribute to it
-__device__ __forceinline__ int row_segments(const int* __restrict__ seg_bucket, const Bands& g, int y, int x,
+// row (y,x) of a bucket: the four quad-key segments that contribute to it; a key's segment is [seg[k], seg[k+1])
+__device__ __forceinline__ int row_segments(const int* __restrict__ seg_bucket, int row_keys, int y, int x,
                                             int (&beg)[4], int& e1, int& e2, int& e3) {
-    // quad (y-1,x-1) -> padded (y, x): this row is its corner 4; quad (y,x) -> padded (y+1, x+1): corner 1
-    const int j4 = y / g.RB, j1 = (y + 1) / g.RB;
-    const int* t4 = seg_bucket + (size_t)j4 * g.tab + (y - j4 * g.RB) * g.row_keys + x;
-    const int* t1 = seg_bucket + (size_t)j1 * g.tab + (y + 1 - j1 * g.RB) * g.row_keys + x + 1;
-    const int sc = __ldg(t1 - 1), sa = __ldg(t1), sb = __ldg(t1 + 1);
-    const int sd = __ldg(t4), se = __ldg(t4 + 1), sf = __ldg(t4 + 2);
-    // accumulation order: corner 1 [sa,sb), corner 2 [sc,sa), corner 3 [se,sf), corner 4 [sd,se)
-    beg[0] = sa; beg[1] = sc; beg[2] = se; beg[3] = sd;
-    e1 = sb - sa;
-    e2 = e1 + (sa - sc);
-    e3 = e2 + (sf - se);
-    return e3 + (se - sd);
+    // quad (y,x) -> padded (y+1, x+1): this row is its corner 1; (y, x-1) -> (y+1, x): corner 2;
+    // (y-1, x) -> (y, x+1): corner 3; (y-1, x-1) -> (y, x): corner 4.  Keys k1-1, k1 and k3-1, k3 are neighbours.
+    const int k1 = (y + 1) * row_keys + x + 1, k3 = y * row_keys + x + 1;
+    const int a0 = __ldg(seg_bucket + k1 - 1), a1 = __ldg(seg_bucket + k1), a2 = __ldg(seg_bucket + k1 + 1);
+    const int c0 = __ldg(seg_bucket + k3 - 1), c1 = __ldg(seg_bucket + k3), c2 = __ldg(seg_bucket + k3 + 1);
+    beg[0] = a1; beg[1] = a0; beg[2] = c1; beg[3] = c0;
+    // accumulation order: corner 1, corner 2, corner 3, corner 4
+    e1 = a2 - a1;
+    e2 = e1 + (a1 - a0);
+    e3 = e2 + (c2 - c1);
+    return e3 + (c1 - c0);
 }
 
 // grid (ceil(num_feat / kClassifyThreads), bs), block kClassifyThreads
@@ -642,11 +832,10 @@ __global__ void __launch_bounds__(kClassifyThreads) dfa_row_classify_kernel(cons
             if (row >= st && row < st + s_tab[i * 3] * s_tab[i * 3 + 1]) cl = i;
         }
         if (cl >= 0) {
-            const int h = s_tab[cl * 3], w = s_tab[cl * 3 + 1], st = s_tab[cl * 3 + 2];
-            const Bands g = band_geometry(h, w, p.NB);
+            const int w = s_tab[cl * 3 + 1], st = s_tab[cl * 3 + 2];
             const int r = row - st, y = r / w, x = r - y * w;
-            if (__ldg(p.cursor + (size_t)b_idx * n_cl + cl) > 0)     // empty bucket: its tables were never written
-                n = row_segments(p.seg + (size_t)b_idx * p.seg_stride + seg_offset(st), g, y, x, beg, e1, e2, e3);
+            if (__ldg(p.cursor + (size_t)b_idx * n_cl + cl) > 0)     // empty bucket: its table was never written
+                n = row_segments(p.seg + (size_t)b_idx * p.seg_stride + seg_offset(st), w + 1, y, x, beg, e1, e2, e3);
         }
     }
     const bool tiny = p.tiny_ok && n > 0 && n <= p.tiny_max;

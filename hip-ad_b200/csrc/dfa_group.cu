@@ -176,3 +176,15 @@ int launch_group_forward(const GroupFwdArgs& a) {
 }
 
 }  // namespace hipad
+
+#ifdef HIPAD_DFA_TRACE
+// development builds: copy (and clear) the per-CTA phase trace of the grouped sample kernels
+extern "C" int hipad_dfa_trace_read_group(long long* host, long long count) {
+    cudaDeviceSynchronize();
+    const int rc = (int)cudaMemcpyFromSymbol(host, hipad::g_trace, sizeof(long long) * (size_t)count);
+    void* sym = nullptr;
+    cudaGetSymbolAddress(&sym, hipad::g_trace);
+    cudaMemset(sym, 0, sizeof(hipad::g_trace));
+    return rc;
+}
+#endif

@@ -118,6 +118,11 @@ __global__ void __launch_bounds__(kW * 32, kMinCtas) dfa_group_kernel(const Grou
     const int p0 = slice * PS;
     const int n_mine = min(PS, NP - p0);
     const int G = p.G, gd = p.C / G;
+    DFA_TRACE_BEGIN((int)blockIdx.x);
+    DFA_TRACE((int)blockIdx.x, 2);
+    DFA_TRACE_DECL(tr5);
+    DFA_TRACE_DECL(tr6);
+    DFA_TRACE_DECL(tr7);
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const GroupSmem& so = p.so;
@@ -192,6 +197,7 @@ __global__ void __launch_bounds__(kW * 32, kMinCtas) dfa_group_kernel(const Grou
         __syncthreads();
     }
 
+    DFA_TRACE((int)blockIdx.x, 3);
     if (kBwd) {
         // zero the weight-gradient rows of invisible pairs (L*G contiguous floats each), all threads, coalesced
         const int lg = L * G;
@@ -287,6 +293,7 @@ __global__ void __launch_bounds__(kW * 32, kMinCtas) dfa_group_kernel(const Grou
     }
     if (tid == 0) s_qstart[n_quads] = (unsigned short)n_items;
     __syncthreads();
+    DFA_TRACE((int)blockIdx.x, 4);
 
     // position of an item in the level-major arrays -> its level
     auto level_of = [&](int pos) { return (pos >= n_pad) + (pos >= 2 * n_pad) + (pos >= 3 * n_pad); };
@@ -349,6 +356,7 @@ __global__ void __launch_bounds__(kW * 32, kMinCtas) dfa_group_kernel(const Grou
 
     for (int qc0 = 0; qc0 < n_quads; qc0 += kQuadChunk) {
         const int nq = min(kQuadChunk, n_quads - qc0);
+        DFA_TRACE_NOW(t5);
 
         // -------------------------------------------------------------- phase 5: per-quad rows (+ forward tables)
         for (int qi = tid; qi < nq; qi += kThreads) {
@@ -385,6 +393,8 @@ __global__ void __launch_bounds__(kW * 32, kMinCtas) dfa_group_kernel(const Grou
             }
         }
         __syncthreads();
+        DFA_TRACE_ACC(tr5, t5);
+        DFA_TRACE_NOW(t6);
 
         // -------------------------------------------------------------- phase 6: gather, one distinct quad at a time
         if constexpr (!kBwd) {
@@ -474,6 +484,8 @@ __global__ void __launch_bounds__(kW * 32, kMinCtas) dfa_group_kernel(const Grou
                 }
             }
             __syncthreads();
+            DFA_TRACE_ACC(tr6, t6);
+            DFA_TRACE_NOW(t7);
 
             // ---------------------------------------------------------- phase 7 (backward): one thread per item
             // g_w[item][g] = sum_k c_k S[g][k];  location-gradient terms of the item = sum_g w[g] * (dx . S[g], dy . S[g])
@@ -508,10 +520,18 @@ __global__ void __launch_bounds__(kW * 32, kMinCtas) dfa_group_kernel(const Grou
                 }
                 s_gxy[it] = make_float2(gx, gy);
             }
+            DFA_TRACE_ACC(tr7, t7);
         }
         __syncthreads();      // the quad tables are rewritten by the next chunk / reused as reduction scratch
+        if constexpr (!kBwd) DFA_TRACE_ACC(tr6, t6);
     }
 
+    DFA_TRACE_V((int)blockIdx.x, 5, tr5);
+    DFA_TRACE_V((int)blockIdx.x, 6, tr6);
+    DFA_TRACE_V((int)blockIdx.x, 7, tr7);
+    DFA_TRACE_V((int)blockIdx.x, 8, n_items);
+    DFA_TRACE_V((int)blockIdx.x, 9, n_quads);
+    DFA_TRACE((int)blockIdx.x, 10);
     if constexpr (!kBwd) {
         // -------------------------------------------------------------- phase 8: cross-warp sum in warp order
 #pragma unroll
@@ -557,6 +577,8 @@ __global__ void __launch_bounds__(kW * 32, kMinCtas) dfa_group_kernel(const Grou
             gloc[l_pair[i]] = make_float2(((t0.x + t1.x) + t2.x) + t3.x, ((t0.y + t1.y) + t2.y) + t3.y);
         }
     }
+    DFA_TRACE((int)blockIdx.x, 11);
+    DFA_TRACE_END((int)blockIdx.x, 12);
 }
 
 }  // namespace hipad

@@ -448,3 +448,32 @@ def test_module_training_path_uses_the_fused_weights_producer(ops):
     assert rel_err(out.detach().cpu().numpy(), ref.detach().cpu().numpy()) <= FP32_TOL
     assert rel_err(g1.cpu().numpy(), inst.grad.cpu().numpy()) <= 2e-5
     assert rel_err(gw1.cpu().numpy(), m.weights_fc.weight.grad.cpu().numpy()) <= 2e-5
+
+
+# ------------------------------------------------------------------------------------- fused inference forward at full size
+@pytest.mark.parametrize("kind,A,P", [("det", 900, 13), ("map", 100, 300), ("plan", 480, 90)])
+@pytest.mark.parametrize("bf16", [False, True])
+def test_fused_forward_stage2_shapes(ops, oracle_mod, kind, A, P, bf16):
+    """the fused kernel (projection + group softmax + aggregation; for map rows a two-pass
+    softmax over 57 600 logits split across a thread-block cluster) at the stage-2 shapes it is benchmarked on, against the
+    reference chain in torch ops feeding the unfused op, and against the C oracle."""
+    import hipad_b200
+    case = H.make_geo_case(31, kind, 1, H.LEVELS_352x640, (352, 640), A=A, P=P)
+    bs, cams, F, C, L, A_, P_, G = case["dims"]
+    feat = dev(case["feat"], torch.bfloat16 if bf16 else None)
+    fm = [feat, dev(case["shapes"]).long(), dev(case["starts"]).long()]
+    logits = dev(case["logits"]).reshape(bs, A, cams, L * P * G) * 2.0
+    kp, pm, wh = dev(case["key_points"]), dev(case["projection_mat"]), dev(case["image_wh"])
+    out, loc = ops.fused_deformable_aggregation(fm, kp, pm, wh, logits, return_locations=True)
+    p2d = hipad_b200.DeformableFeatureAggregation.project_points(kp, pm, wh).permute(0, 2, 3, 1, 4).contiguous()
+    assert rel_err(loc.cpu().numpy(), p2d.cpu().numpy()) <= 1e-5
+    assert float((((loc > 0) & (loc < 1)).all(-1) != ((p2d > 0) & (p2d < 1)).all(-1)).float().mean()) <= 1e-3
+    w = logits.reshape(bs, A, -1, G).softmax(dim=-2).reshape(bs, A, cams, L, P, G).permute(0, 1, 4, 2, 3, 5).contiguous()
+    ref = ops.deformable_aggregation_function(*fm, loc, w)           # same locations, torch softmax, unfused op
+    assert rel_err(out.cpu().numpy(), ref.cpu().numpy()) <= FP32_TOL
+    f_cpu = feat.float().cpu().numpy()
+    cpu = oracle_mod.forward(f_cpu, case["shapes"], case["starts"], loc.cpu().numpy(), w.cpu().numpy())
+    assert rel_err(out.cpu().numpy(), cpu) <= FP32_TOL
+    # and the training-side producer gives the same weights as torch's softmax + permute
+    w2 = ops.aggregation_weights(logits, cams, L, P, G)
+    assert rel_err(w2.cpu().numpy(), w.cpu().numpy()) <= 2e-6
