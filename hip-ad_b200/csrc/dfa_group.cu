@@ -19,13 +19,25 @@ inline int group_ps_max(bool bwd) {
     return (v >= 16 && v <= kGroupMaxPS) ? v : dflt;
 }
 
-template <typename T, int V, int NCH, bool kBwd, int kW, int kDepth, int kMinCtas>
-int launch_inst(const GroupParams& gp, int grid, size_t smem, cudaStream_t st) {
-    auto kern = dfa_group_kernel<T, V, NCH, kBwd, kW, kDepth, kMinCtas>;
+template <typename T, int V, int NCH, bool kBwd, int kW, int kDepth, int kMinCtas, int kG>
+int launch_inst_g(const GroupParams& gp, int grid, size_t smem, cudaStream_t st) {
+    auto kern = dfa_group_kernel<T, V, NCH, kBwd, kW, kDepth, kMinCtas, kG>;
     cudaError_t e = ensure_smem(kern, smem);
     if (e != cudaSuccess) return (int)e;
     kern<<<grid, kW * 32, smem, st>>>(gp);
     return (int)cudaGetLastError();
+}
+
+// G = 8 (every aggregation module of the reference's configs) gets the instantiation with G folded in.  Measured on the
+// stage-2 layer, bs = 1 / 4: backward sample kernel f32 119 -> 107 / 421 -> 381 us, bf16 98 -> 90 us; forward bf16
+// 93 -> 84 us; the fp32 FORWARD is slower with it (78 -> 84 / 251 -> 271 us: ptxas spills at its 64-register cap) and
+// keeps the generic instantiation.
+template <typename T, int V, int NCH, bool kBwd, int kW, int kDepth, int kMinCtas>
+int launch_inst(const GroupParams& gp, int grid, size_t smem, cudaStream_t st) {
+    constexpr bool kFold = kBwd || sizeof(T) == 2;
+    if (kFold && gp.G == 8 && hipad_env_int("HIPAD_DFA_GROUP_GENERIC_G", 0) == 0)
+        return launch_inst_g<T, V, NCH, kBwd, kW, kDepth, kMinCtas, kFold ? 8 : 0>(gp, grid, smem, st);
+    return launch_inst_g<T, V, NCH, kBwd, kW, kDepth, kMinCtas, 0>(gp, grid, smem, st);
 }
 
 // deep = 2 quads in flight per warp for fp32 rows (4 for packed bf16), 128 registers, 4 CTAs of 4 warps per SM;
@@ -139,6 +151,8 @@ int launch_group_sample(bool bwd, ElemType t, const GroupParams& gp, long long u
     g.so = group_smem_layout(bwd, gp.ps_max, nch * 32 * V, kw);
     const size_t smem = (size_t)g.so.total;
     if (smem > kSampleSmemBudget) return -2;
+    g.zero_per = (units > 0) ? (g.zero_n16 + units - 1) / units : 0;
+    if (g.zero_per >= (1LL << 31)) return -2;
     // measured (stage-2 layer, f32): forward 82 us at 8 CTAs/SM vs 89 at 6 (bs=4: 257 vs 296); the backward needs more
     // registers (64 spills inside its epilogue) and is faster at 6 (118 vs 129 us)
     int variant = hipad_env_int("HIPAD_DFA_GROUP_CTAS", bwd ? 6 : 8) >= 8 ? 2 : 1;

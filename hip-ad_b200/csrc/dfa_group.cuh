@@ -84,6 +84,7 @@ struct GroupParams {
     int* tickets;            // forward workspace: [sum over calls with S>1 of bs*A], zeroed before the launch
     uint4* zero_ptr;         // backward: dense buffer this launch zero-fills on the side (or null)
     long long zero_n16;
+    long long zero_per;      // 16-byte units per CTA: ceil(zero_n16 / grid), < 2^31 (filled by launch_group_sample)
     int ncalls, bs, cams, num_feat, C, G, ps_max, pad_;
     GroupSmem so;            // shared-memory carve-up (filled by the host: the kernel reads the offsets as constants)
     GroupCall calls[kMaxGroupCalls];
@@ -95,7 +96,10 @@ struct ItemGeo {
 
 // kDepth: distinct quads whose rows are in flight per warp (registers: kDepth * 32 for fp32 C = 256);
 // kMinCtas: CTAs per SM the register allocation must allow
-template <typename T, int V, int NCH, bool kBwd, int kW, int kDepth, int kMinCtas>
+// kG: the number of channel groups when known at compile time (0 = read it from the parameters): with G fixed, the lanes
+// per group, the butterfly's shuffle distances and the weight-row length fold into constants (the backward kernel spends
+// a quarter of its instructions on that butterfly)
+template <typename T, int V, int NCH, bool kBwd, int kW, int kDepth, int kMinCtas, int kG = 0>
 __global__ void __launch_bounds__(kW * 32, kMinCtas) dfa_group_kernel(const GroupParams p) {
     constexpr int kThreads = kW * 32;
     constexpr int L = kGroupL;
@@ -117,7 +121,8 @@ __global__ void __launch_bounds__(kW * 32, kMinCtas) dfa_group_kernel(const Grou
     const int b = ba / A, a = ba - b * A;
     const int p0 = slice * PS;
     const int n_mine = min(PS, NP - p0);
-    const int G = p.G, gd = p.C / G;
+    const int G = (kG > 0) ? kG : p.G;
+    const int gd = (NCH * 32 * V) / G;                     // C == NCH*32*V (checked on the host)
     DFA_TRACE_BEGIN((int)blockIdx.x);
     DFA_TRACE((int)blockIdx.x, 2);
     DFA_TRACE_DECL(tr5);
@@ -148,11 +153,19 @@ __global__ void __launch_bounds__(kW * 32, kMinCtas) dfa_group_kernel(const Grou
     if (kBwd && p.zero_n16 > 0) {
         // dense zero fill of the feature gradient, 1/gridDim of it per CTA: fire-and-forget stores that drain
         // while this CTA waits on its gather loads
-        const long long per = (p.zero_n16 + gridDim.x - 1) / gridDim.x;
-        const long long z0 = (long long)blockIdx.x * per;
-        const long long z1 = (z0 + per < p.zero_n16) ? z0 + per : p.zero_n16;
+        const long long z0 = (long long)blockIdx.x * p.zero_per;          // zero_per = ceil(zero_n16 / gridDim.x), host
+        const long long left = p.zero_n16 - z0;
+        const int cnt = (int)(left < p.zero_per ? (left > 0 ? left : 0) : p.zero_per);
+        uint4* zp = p.zero_ptr + z0;
         const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-        for (long long i = z0 + tid; i < z1; i += kThreads) p.zero_ptr[i] = z;
+        int i = tid;
+        for (; i + 3 * kThreads < cnt; i += 4 * kThreads) {
+            zp[i] = z;
+            zp[i + kThreads] = z;
+            zp[i + 2 * kThreads] = z;
+            zp[i + 3 * kThreads] = z;
+        }
+        for (; i < cnt; i += kThreads) zp[i] = z;
     }
     if (tid == 0) {
         // The weights of the unit's pairs (L*G floats each, contiguous) are needed a few microseconds from now (phase 5
