@@ -45,7 +45,13 @@ SideStream* acquire_side_stream(cudaStream_t main) {
     }
     if (st != cudaStreamCaptureStatusNone) return nullptr;   // never create resources inside a capture
     SideStream s;
-    if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    // The chain is a few hundred latency-bound CTAs; the sample kernel beside it has thousands.  At the highest stream
+    // priority the chain's CTAs take the SM slots that free up first instead of queueing behind the sample kernel's
+    // (measured, stage-2 layer backward, bs = 1 / 4: 264 -> 235 us, 875 -> 848 us; HIPAD_DFA_SIDE_PRIORITY=0 turns it off).
+    int prio_lo = 0, prio_hi = 0;
+    if (cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi) != cudaSuccess) { cudaGetLastError(); prio_hi = 0; }
+    if (hipad_env_int("HIPAD_DFA_SIDE_PRIORITY", 1) == 0) prio_hi = 0;
+    if (cudaStreamCreateWithPriority(&s.stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess) { cudaGetLastError(); return nullptr; }
     if (cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); return nullptr; }
     return &pool.emplace(std::make_pair(dev, main), s).first->second;
@@ -240,74 +246,84 @@ int launch_group_backward(const GroupBwdArgs& a) {
     };
 
     // ---- K1: sample-major, g_w + g_loc (fully written); zero-fills g_feat on the side when it has the CTAs
-    if (a.stage_mask & 1) {
-        const bool want_zero = a.g_feat != nullptr && !a.accumulate;
-        const bool vec_ok = (gfeat_bytes % 16 == 0) && (reinterpret_cast<uintptr_t>(a.g_feat) % 16 == 0);
-        bool zero_done = !want_zero;
-        auto separate_zero = [&]() -> int {
-            if (vec_ok) {
-                dfa_zero_kernel<<<148 * 16, 256, 0, a.stream>>>(reinterpret_cast<uint4*>(a.g_feat), (long long)(gfeat_bytes / 16));
-                return (int)cudaGetLastError();
-            }
-            return (int)cudaMemsetAsync(a.g_feat, 0, gfeat_bytes, a.stream);
-        };
-        if (grouped) {
-            const GroupPlan pl = plan_group(true, a.calls, a.ncalls, d.bs, d.cams, d.C, 0);
-            GroupParams gpk = {};
-            gpk.feat = a.feat; gpk.shapes = a.shapes; gpk.starts = a.starts;
-            int rc = fill_group_params(gpk, pl, a.calls, a.ncalls, d.bs, d.cams, d.num_feat, d.C, d.G,
-                                       ids.a_total * d.C, nullptr, a.grad_out);
-            if (rc != 0) return finish(rc);
-            if (want_zero) {
-                // (measured and not kept: giving a launch too small to fold the fill in -- the ego call -- the helper
-                // stream for its sample kernel as well: 45 vs 41 us; in a group the ego call costs nothing anyway)
-                if (vec_ok && pl.units >= 2 * 148 && !a.separate_zero_fill) {
-                    gpk.zero_ptr = reinterpret_cast<uint4*>(a.g_feat);
-                    gpk.zero_n16 = (long long)(gfeat_bytes / 16);
-                } else if (int e = separate_zero()) {
-                    return finish(e);
+    auto run_k1 = [&]() -> int {
+        if (a.stage_mask & 1) {
+            const bool want_zero = a.g_feat != nullptr && !a.accumulate;
+            const bool vec_ok = (gfeat_bytes % 16 == 0) && (reinterpret_cast<uintptr_t>(a.g_feat) % 16 == 0);
+            bool zero_done = !want_zero;
+            auto separate_zero = [&]() -> int {
+                if (vec_ok) {
+                    dfa_zero_kernel<<<148 * 16, 256, 0, a.stream>>>(reinterpret_cast<uint4*>(a.g_feat), (long long)(gfeat_bytes / 16));
+                    return (int)cudaGetLastError();
                 }
-                zero_done = true;
-            }
-            rc = launch_group_sample(true, a.type, gpk, pl.units, a.stream);
-            if (rc != 0) return finish(rc);
-        } else {
-            for (int k = 0; k < a.ncalls; ++k) {
-                Dims dk = d;
-                dk.A = a.calls[k].A; dk.P = a.calls[k].P;
-                SampleParams p = {};
-                p.feat = a.feat; p.shapes = a.shapes; p.starts = a.starts;
-                p.loc = a.calls[k].loc; p.weights = a.calls[k].weights;
-                p.grad_out = a.grad_out + (size_t)ids.anchor_begin[k] * d.C;     // ncalls == 1 or bs == 1: contiguous
-                p.g_loc = a.calls[k].g_loc; p.g_w = a.calls[k].g_w;
-                p.d = dk;
-                const int NP = dk.P * dk.cams;
-                const long long rows = (long long)dk.bs * dk.A;
-                p.S = choose_slices(rows, NP, 8 * 148, sample_smem_per_pair(kBwd, dk.L), /*max_slices=*/1 << 20);
-                if (p.S == 0) return finish(-2);
-                p.PS = (NP + p.S - 1) / p.S;
-                const long long grid = rows * p.S;
-                if (grid > 0x7fffffffLL) return finish(-2);
-                const int warps = choose_sample_warps(grid, dk.G);
-                const size_t smem = sample_smem_for(kBwd, dk, ks, a.type, p.PS, warps);
-                if (smem > kSampleSmemBudget) return finish(-2);
-                if (!zero_done) {
-                    if (vec_ok && grid >= 2 * 148 && !a.separate_zero_fill) {
-                        p.zero_ptr = reinterpret_cast<uint4*>(a.g_feat);
-                        p.zero_n16 = (long long)(gfeat_bytes / 16);
+                return (int)cudaMemsetAsync(a.g_feat, 0, gfeat_bytes, a.stream);
+            };
+            if (grouped) {
+                const GroupPlan pl = plan_group(true, a.calls, a.ncalls, d.bs, d.cams, d.C, 0);
+                GroupParams gpk = {};
+                gpk.feat = a.feat; gpk.shapes = a.shapes; gpk.starts = a.starts;
+                int rc = fill_group_params(gpk, pl, a.calls, a.ncalls, d.bs, d.cams, d.num_feat, d.C, d.G,
+                                           ids.a_total * d.C, nullptr, a.grad_out);
+                if (rc != 0) return rc;
+                if (want_zero) {
+                    // (measured and not kept: giving a launch too small to fold the fill in -- the ego call -- the helper
+                    // stream for its sample kernel as well: 45 vs 41 us; in a group the ego call costs nothing anyway)
+                    // a launch of >= 2 CTAs per SM carries the fill (padded with fill-only CTAs up to 12 per SM: det call
+                    // backward 115 -> 104 us); below that (ego: 1 unit) a dedicated fill kernel is faster (37 vs 43 us)
+                    if (vec_ok && pl.units >= 2 * 148 && !a.separate_zero_fill) {
+                        gpk.zero_ptr = reinterpret_cast<uint4*>(a.g_feat);
+                        gpk.zero_n16 = (long long)(gfeat_bytes / 16);
                     } else if (int e = separate_zero()) {
-                        return finish(e);
+                        return e;
                     }
                     zero_done = true;
                 }
-                const int rc = (a.type == kF32)
-                                   ? dispatch_sample<float, kBwd, false>(p, ks, warps, (int)grid, smem, a.stream)
-                                   : dispatch_sample<__nv_bfloat16, kBwd, false>(p, ks, warps, (int)grid, smem, a.stream);
-                if (rc != 0) return finish(rc);
+                rc = launch_group_sample(true, a.type, gpk, pl.units, a.stream);
+                if (rc != 0) return rc;
+            } else {
+                for (int k = 0; k < a.ncalls; ++k) {
+                    Dims dk = d;
+                    dk.A = a.calls[k].A; dk.P = a.calls[k].P;
+                    SampleParams p = {};
+                    p.feat = a.feat; p.shapes = a.shapes; p.starts = a.starts;
+                    p.loc = a.calls[k].loc; p.weights = a.calls[k].weights;
+                    p.grad_out = a.grad_out + (size_t)ids.anchor_begin[k] * d.C;     // ncalls == 1 or bs == 1: contiguous
+                    p.g_loc = a.calls[k].g_loc; p.g_w = a.calls[k].g_w;
+                    p.d = dk;
+                    const int NP = dk.P * dk.cams;
+                    const long long rows = (long long)dk.bs * dk.A;
+                    p.S = choose_slices(rows, NP, 8 * 148, sample_smem_per_pair(kBwd, dk.L), /*max_slices=*/1 << 20);
+                    if (p.S == 0) return -2;
+                    p.PS = (NP + p.S - 1) / p.S;
+                    const long long grid = rows * p.S;
+                    if (grid > 0x7fffffffLL) return -2;
+                    const int warps = choose_sample_warps(grid, dk.G);
+                    const size_t smem = sample_smem_for(kBwd, dk, ks, a.type, p.PS, warps);
+                    if (smem > kSampleSmemBudget) return -2;
+                    if (!zero_done) {
+                        if (vec_ok && grid >= 2 * 148 && !a.separate_zero_fill) {
+                            p.zero_ptr = reinterpret_cast<uint4*>(a.g_feat);
+                            p.zero_n16 = (long long)(gfeat_bytes / 16);
+                        } else if (int e = separate_zero()) {
+                            return e;
+                        }
+                        zero_done = true;
+                    }
+                    const int rc = (a.type == kF32)
+                                       ? dispatch_sample<float, kBwd, false>(p, ks, warps, (int)grid, smem, a.stream)
+                                       : dispatch_sample<__nv_bfloat16, kBwd, false>(p, ks, warps, (int)grid, smem, a.stream);
+                    if (rc != 0) return rc;
+                }
             }
+            if (int e = debug_sync("sample-major backward kernel", a.stream)) return e;
         }
-        if (int e = debug_sync("sample-major backward kernel", a.stream)) return finish(e);
-    }
+        return 0;
+    };
+    // HIPAD_DFA_CHAIN_FIRST=1 issues the chain's (short) launches before the sample kernel.  Measured with the chain at high
+    // priority, stage-2 layer backward, bs = 1 / 4: sample kernel first 235 / 848 us, chain first 238 / 872 us (default: off).
+    const bool chain_first = side != nullptr && hipad_env_int("HIPAD_DFA_CHAIN_FIRST", 0) != 0;
+    if (!chain_first)
+        if (int rc1 = run_k1()) return finish(rc1);
     if (a.g_feat == nullptr) return finish(0);   // caller does not need the feature-map gradient
 
     // ---- K2: visible-sample compaction, then per-(b,cam,level,band) sort by quad key
@@ -402,6 +418,8 @@ int launch_group_backward(const GroupBwdArgs& a) {
     if (e != cudaSuccess) return finish((int)e);
     if (int e2 = debug_sync("row classification", chain)) return finish(e2);
     if (a.classify_only) return finish(0);
+    if (chain_first)
+        if (int rc1 = run_k1()) return finish(rc1);
     // join: the reduce needs the work lists (helper stream) and the zero-filled g_feat (caller's)
     if (int ej = finish(0)) return ej;
     const int rc = (a.type == kF32 || a.g_feat_f32) ? launch_reduce<float>(gp, ks_g, a.stream)

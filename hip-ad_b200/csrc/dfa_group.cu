@@ -1,5 +1,6 @@
 // dfa_group.cu — host side of the grouped sample-major kernel (dfa_group.cuh): unit planning, forward launcher,
 // and the sample-major half of the grouped backward (called from dfa_backward.cu).
+#include <algorithm>
 #include "dfa_dispatch.cuh"
 #include "dfa_group.cuh"
 #include "dfa_group_host.h"
@@ -8,9 +9,17 @@ namespace hipad {
 
 namespace {
 constexpr size_t kAlignG = 256;
+constexpr long long kZeroFillMinCtas = 148 * 12;   // CTAs of a launch that carries a dense zero fill (6 per SM, two rounds)
 inline size_t align_g(size_t v) { return (v + kAlignG - 1) / kAlignG * kAlignG; }
 
-inline int group_warps() { return 4; }     // measured: 8-warp CTAs are 1.3x slower (r2b)
+#ifndef HIPAD_GROUP_WARPS
+#define HIPAD_GROUP_WARPS 4
+#endif
+// warps per unit.  Measured on the stage-2 layer: 8-warp CTAs 1.3x slower (r2b); 2-warp CTAs at twice the CTAs per SM, 48- to
+// 96-pair units: forward 101 vs 74 us, backward sample kernel 116-122 vs 103 us (x5)
+constexpr int kGW = HIPAD_GROUP_WARPS;
+constexpr int kGM = 4 / kGW;                 // CTAs per SM scale with the CTA size
+inline int group_warps() { return kGW; }
 // (p,cam) pairs per unit.  Longer units find more key points of an anchor in the same quad (fewer gathers) but hold
 // more shared memory, which is taken from the L1 cache the gather lives on
 inline int group_ps_max(bool bwd) {
@@ -48,17 +57,17 @@ template <bool kBwd>
 int dispatch(ElemType t, int variant, const GroupParams& gp, int grid, size_t smem, cudaStream_t st) {
     // variant 0: deep pipeline, 4 CTAs/SM; 1: shallow, 6 CTAs/SM (<= 80 registers); 2: shallow, 8 CTAs/SM (64 registers)
     if (t == kF32) {
-        if (gp.C == 128) return launch_inst<float, 4, 1, kBwd, 4, 2, 5>(gp, grid, smem, st);
+        if (gp.C == 128) return launch_inst<float, 4, 1, kBwd, kGW, 2, 5 * kGM>(gp, grid, smem, st);
         if (gp.C == 256) {
-            if (variant == 0) return launch_inst<float, 4, 2, kBwd, 4, 2, 4>(gp, grid, smem, st);
-            if (variant == 2) return launch_inst<float, 4, 2, kBwd, 4, 1, 8>(gp, grid, smem, st);
-            return launch_inst<float, 4, 2, kBwd, 4, 1, 6>(gp, grid, smem, st);
+            if (variant == 0) return launch_inst<float, 4, 2, kBwd, kGW, 2, 4 * kGM>(gp, grid, smem, st);
+            if (variant == 2) return launch_inst<float, 4, 2, kBwd, kGW, 1, 8 * kGM>(gp, grid, smem, st);
+            return launch_inst<float, 4, 2, kBwd, kGW, 1, 6 * kGM>(gp, grid, smem, st);
         }
     } else {
         if (gp.C == 256) {
-            if (variant == 0) return launch_inst<__nv_bfloat16, 8, 1, kBwd, 4, 4, 4>(gp, grid, smem, st);
-            if (variant == 2) return launch_inst<__nv_bfloat16, 8, 1, kBwd, 4, 2, 8>(gp, grid, smem, st);
-            return launch_inst<__nv_bfloat16, 8, 1, kBwd, 4, 2, 5>(gp, grid, smem, st);
+            if (variant == 0) return launch_inst<__nv_bfloat16, 8, 1, kBwd, kGW, 4, 4 * kGM>(gp, grid, smem, st);
+            if (variant == 2) return launch_inst<__nv_bfloat16, 8, 1, kBwd, kGW, 2, 8 * kGM>(gp, grid, smem, st);
+            return launch_inst<__nv_bfloat16, 8, 1, kBwd, kGW, 2, 5 * kGM>(gp, grid, smem, st);
         }
     }
     return -2;
@@ -94,6 +103,16 @@ GroupPlan plan_group(bool bwd, const CallDesc* calls, int ncalls, int bs, int ca
         S = (NP + PS - 1) / PS;                       // no empty slice
         pl.S[k] = S;
         pl.PS[k] = PS;
+        pl.order[k] = k;
+        if (PS > ps_max) ps_max = PS;
+    }
+    // CTAs are dispatched in index order: calls with the longest units go first, so the launch drains on short units
+    // (no result depends on the order: every sum is ordered inside its unit / row)
+    if (hipad_env_int("HIPAD_DFA_GROUP_ORDER", 1) != 0)
+        std::stable_sort(pl.order, pl.order + ncalls, [&](int x, int y) { return pl.PS[x] > pl.PS[y]; });
+    for (int i = 0; i < ncalls; ++i) {
+        const int k = pl.order[i];
+        const int S = pl.S[k];
         pl.unit_begin[k] = units;
         units += (long long)bs * calls[k].A * S;
         if (!bwd && S > 1) {
@@ -102,7 +121,6 @@ GroupPlan plan_group(bool bwd, const CallDesc* calls, int ncalls, int bs, int ca
             parts += (long long)bs * calls[k].A * S;
             rows += (long long)bs * calls[k].A;
         }
-        if (PS > ps_max) ps_max = PS;
     }
     pl.units = units;
     pl.parts = parts;
@@ -125,18 +143,20 @@ int fill_group_params(GroupParams& gp, const GroupPlan& pl, const CallDesc* call
     if (pl.units <= 0 || pl.units > 0x7fffffffLL) return -2;
     gp.ncalls = ncalls; gp.bs = bs; gp.cams = cams; gp.num_feat = num_feat; gp.C = C; gp.G = G;
     gp.ps_max = pl.ps_max;
-    long long a_begin = 0;
-    for (int k = 0; k < ncalls; ++k) {
-        GroupCall& c = gp.calls[k];
+    long long a_begin[kMaxCalls];
+    long long a_sum = 0;
+    for (int k = 0; k < ncalls; ++k) { a_begin[k] = a_sum; a_sum += calls[k].A; }
+    for (int i = 0; i < ncalls; ++i) {
+        const int k = pl.order[i];
+        GroupCall& c = gp.calls[i];                  // table slots in unit order (the kernel finds its call by unit_begin)
         c.loc = calls[k].loc; c.weights = calls[k].weights; c.g_loc = calls[k].g_loc; c.g_w = calls[k].g_w;
-        c.out = out ? out + a_begin * C : nullptr;
-        c.grad_out = grad_out ? grad_out + a_begin * C : nullptr;
+        c.out = out ? out + a_begin[k] * C : nullptr;
+        c.grad_out = grad_out ? grad_out + a_begin[k] * C : nullptr;
         c.io_bstride = io_bstride;
         c.A = calls[k].A; c.P = calls[k].P; c.S = pl.S[k]; c.PS = pl.PS[k];
         c.unit_begin = (int)pl.unit_begin[k];
         c.part_begin = (int)pl.part_begin[k];
         c.row_begin = (int)pl.row_begin[k];
-        a_begin += calls[k].A;
         // 32-bit element offsets inside one call's tensors are not assumed anywhere; pair counts are ints
         if ((long long)calls[k].P * cams > (1 << 24)) return -2;
     }
@@ -151,13 +171,17 @@ int launch_group_sample(bool bwd, ElemType t, const GroupParams& gp, long long u
     g.so = group_smem_layout(bwd, gp.ps_max, nch * 32 * V, kw);
     const size_t smem = (size_t)g.so.total;
     if (smem > kSampleSmemBudget) return -2;
-    g.zero_per = (units > 0) ? (g.zero_n16 + units - 1) / units : 0;
+    // a launch that carries the dense zero fill is padded with fill-only CTAs (the fill then runs on the whole machine)
+    long long grid = units;
+    if (bwd && g.zero_n16 > 0 && grid < kZeroFillMinCtas) grid = kZeroFillMinCtas;
+    g.units = (int)units;
+    g.zero_per = (grid > 0) ? (g.zero_n16 + grid - 1) / grid : 0;
     if (g.zero_per >= (1LL << 31)) return -2;
     // measured (stage-2 layer, f32): forward 82 us at 8 CTAs/SM vs 89 at 6 (bs=4: 257 vs 296); the backward needs more
     // registers (64 spills inside its epilogue) and is faster at 6 (118 vs 129 us)
     int variant = hipad_env_int("HIPAD_DFA_GROUP_CTAS", bwd ? 6 : 8) >= 8 ? 2 : 1;
     if (hipad_env_int("HIPAD_DFA_GROUP_DEEP", 0) != 0) variant = 0;
-    return bwd ? dispatch<true>(t, variant, g, (int)units, smem, st) : dispatch<false>(t, variant, g, (int)units, smem, st);
+    return bwd ? dispatch<true>(t, variant, g, (int)grid, smem, st) : dispatch<false>(t, variant, g, (int)units, smem, st);
 }
 
 int launch_group_forward(const GroupFwdArgs& a) {

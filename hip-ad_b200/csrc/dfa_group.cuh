@@ -85,7 +85,8 @@ struct GroupParams {
     uint4* zero_ptr;         // backward: dense buffer this launch zero-fills on the side (or null)
     long long zero_n16;
     long long zero_per;      // 16-byte units per CTA: ceil(zero_n16 / grid), < 2^31 (filled by launch_group_sample)
-    int ncalls, bs, cams, num_feat, C, G, ps_max, pad_;
+    int ncalls, bs, cams, num_feat, C, G, ps_max;
+    int units;               // CTAs [units, gridDim.x) exist only for the zero fill (launches with few units)
     GroupSmem so;            // shared-memory carve-up (filled by the host: the kernel reads the offsets as constants)
     GroupCall calls[kMaxGroupCalls];
 };
@@ -166,6 +167,7 @@ __global__ void __launch_bounds__(kW * 32, kMinCtas) dfa_group_kernel(const Grou
             zp[i + 3 * kThreads] = z;
         }
         for (; i < cnt; i += kThreads) zp[i] = z;
+        if ((int)blockIdx.x >= p.units) return;      // a CTA added to the launch for the fill alone (block-uniform)
     }
     if (tid == 0) {
         // The weights of the unit's pairs (L*G floats each, contiguous) are needed a few microseconds from now (phase 5

@@ -11,6 +11,7 @@ struct GroupPlan {
     long long unit_begin[kMaxCalls], part_begin[kMaxCalls], row_begin[kMaxCalls];
     long long units, parts, rows;
     int ps_max;
+    int order[kMaxCalls];    // slot i of the kernel's call table holds call order[i] (units are dealt slot by slot)
     size_t partial_bytes, ticket_bytes;
 };
 
