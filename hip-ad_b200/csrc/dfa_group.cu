@@ -9,7 +9,8 @@ namespace hipad {
 
 namespace {
 constexpr size_t kAlignG = 256;
-constexpr long long kZeroFillMinCtas = 148 * 12;   // CTAs of a launch that carries a dense zero fill (6 per SM, two rounds)
+// CTAs of a launch that carries a dense zero fill (measured, det call backward: 8 / 12 / 18 / 24 per SM -> 113 / 106 / 104 / 102 us)
+constexpr long long kZeroFillMinCtas = 148 * 24;
 inline size_t align_g(size_t v) { return (v + kAlignG - 1) / kAlignG * kAlignG; }
 
 #ifndef HIPAD_GROUP_WARPS
@@ -173,7 +174,8 @@ int launch_group_sample(bool bwd, ElemType t, const GroupParams& gp, long long u
     if (smem > kSampleSmemBudget) return -2;
     // a launch that carries the dense zero fill is padded with fill-only CTAs (the fill then runs on the whole machine)
     long long grid = units;
-    if (bwd && g.zero_n16 > 0 && grid < kZeroFillMinCtas) grid = kZeroFillMinCtas;
+    const long long fill_ctas = 148LL * hipad_env_int("HIPAD_DFA_FILL_CTAS_PER_SM", (int)(kZeroFillMinCtas / 148));
+    if (bwd && g.zero_n16 > 0 && grid < fill_ctas) grid = fill_ctas;
     g.units = (int)units;
     g.zero_per = (grid > 0) ? (g.zero_n16 + grid - 1) / grid : 0;
     if (g.zero_per >= (1LL << 31)) return -2;

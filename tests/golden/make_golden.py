@@ -236,7 +236,9 @@ def oracle_daf(col_feats, spatial_shape, scale_start_index, sampling_location, w
 
 
 def module_case(regs, blocks, ops, name, seed, kind, embed, G, level_hw, final_hw, n_keep, bs=1,
-                via_oracle_daf=False):
+                via_oracle_daf=False, store_f16=False, n_perturb=2, allow_band=False):
+    """store_f16: the parameter matrices and feature maps are rounded to fp16-representable values BEFORE the
+    reference runs (in fp32) and stored as fp16 -- exact, half the fixture size (the C=256 cases)."""
     rng = np.random.default_rng(seed)
     torch.manual_seed(seed)
     cams, L = 6, len(level_hw)
@@ -251,7 +253,7 @@ def module_case(regs, blocks, ops, name, seed, kind, embed, G, level_hw, final_h
         plan = np.load(os.path.join(REF, "data/kmeans/b2d_plan_spat_6x8_5m.npy")).astype(np.float32)
         anchors = plan.reshape(plan.shape[0], -1)
         anchors = np.concatenate([anchors + rng.normal(0, 0.4, anchors.shape).astype(np.float32)
-                                  for _ in range(2)])
+                                  for _ in range(n_perturb)])
     m = blocks.DeformableFeatureAggregation(
         embed_dims=embed, num_groups=G, num_levels=L, num_cams=cams, attn_drop=0.15,
         use_deformable_func=False, use_camera_embed=True, residual_mode="cat", kps_generator=kps)
@@ -261,6 +263,8 @@ def module_case(regs, blocks, ops, name, seed, kind, embed, G, level_hw, final_h
     for p in m.parameters():            # reference init zeroes weights_fc: make it non-trivial
         if p.requires_grad:
             nn.init.normal_(p, std=0.3 if p.ndim > 1 else 0.1)
+            if store_f16 and p.ndim > 1:
+                p.data = p.data.half().float()
     m.eval()
     P = m.num_pts
     n_all = anchors.shape[0]
@@ -273,7 +277,7 @@ def module_case(regs, blocks, ops, name, seed, kind, embed, G, level_hw, final_h
         kp_all = m.kps_generator(anchor, emb, inst)
         p2d = m.project_points(kp_all, proj, wh)                        # [bs,cams,A,P,2]
         bad = in_band(p2d, level_hw).any(dim=3).any(dim=1).any(dim=0)   # per anchor
-        if via_oracle_daf:
+        if via_oracle_daf or allow_band:     # allow_band: fixture for the torch branch / host logic only
             bad[:] = False
         vis = ((p2d > 0) & (p2d < 1)).all(-1).any(dim=3).any(dim=1).any(dim=0)
     good = torch.nonzero(~bad & vis).flatten()[:n_keep]
@@ -281,44 +285,64 @@ def module_case(regs, blocks, ops, name, seed, kind, embed, G, level_hw, final_h
     assert len(good) == n_keep, (name, len(good))
     anchor, inst, emb = anchor[:, good], inst[:, good], emb[:, good]
     fmaps = [torch.tensor(rng.standard_normal((bs, cams, embed, h, w)).astype(np.float32)) for h, w in level_hw]
+    if store_f16:
+        fmaps = [f.half().float() for f in fmaps]
     metas = dict(projection_mat=proj, image_wh=wh)
     with torch.no_grad():
         out = m(inst, anchor, emb, ops.feature_maps_format(fmaps) if via_oracle_daf else fmaps, metas)
         key_points = m.kps_generator(anchor, emb, inst)
         weights = m._get_weights(inst, emb, metas)
         p2d = m.project_points(key_points, proj, wh)
-        assert via_oracle_daf or not in_band(p2d, level_hw).any()
+        assert via_oracle_daf or allow_band or not in_band(p2d, level_hw).any()
     fmt = ops.feature_maps_format(fmaps)
     inv = ops.feature_maps_format(fmt, inverse=True)
     assert all(torch.equal(a, b) for a, b in zip(inv[0], fmaps))
-    sd = {"sd." + k: v.numpy() for k, v in m.state_dict().items()}
+    big = {n for n, p in m.named_parameters() if p.requires_grad and p.ndim > 1} if store_f16 else set()
+    sd = {"sd." + k: (v.numpy().astype(np.float16) if k in big else v.numpy()) for k, v in m.state_dict().items()}
+    for k in big:
+        assert np.array_equal(sd["sd." + k].astype(np.float32), m.state_dict()[k].numpy())
     np.savez_compressed(
         os.path.join(OUT, name + ".npz"), **sd,
-        **{f"fmap{i}": fm.numpy() for i, fm in enumerate(fmaps)},
+        **{f"fmap{i}": (fm.numpy().astype(np.float16) if store_f16 else fm.numpy()) for i, fm in enumerate(fmaps)},
         instance_feature=inst.numpy(), anchor=anchor.numpy(), anchor_embed=emb.numpy(),
         projection_mat=proj.numpy(), image_wh=wh.numpy(), out=out.numpy(),
         key_points=key_points.numpy(), weights=weights.numpy(), points_2d=p2d.numpy(),
         col_feats_checksum=np.float64(fmt[0].double().sum().item()),
         col_feats_shape=np.array(fmt[0].shape), spatial_shape=fmt[1].numpy(),
         scale_start_index=fmt[2].numpy(), num_groups=np.int32(G), kind=np.array(kind),
-        via_oracle_daf=np.bool_(via_oracle_daf))
+        via_oracle_daf=np.bool_(via_oracle_daf), band_free=np.bool_(not allow_band))
     print(name, "out", tuple(out.shape), "P", P, "valid frac",
           float(((p2d > 0) & (p2d < 1)).all(-1).float().mean()))
 
 
 def main():
+    only = set(sys.argv[1:])           # optional: names of the fixtures to (re)generate
+    want = lambda n: not only or n in only
     regs, blocks, det_blocks, map_blocks, ops = load_reference()
     torch.set_num_threads(8)
-    op_case(blocks, "op_small", 1, bs=2, cams=3, level_hw=[(12, 20), (6, 10), (3, 5)], C=32, G=4, A=10, P=5)
-    op_case(blocks, "op_c256", 2, bs=1, cams=6, level_hw=[(8, 12), (4, 6), (2, 3), (1, 2)], C=256, G=8, A=12, P=13)
-    op_case(blocks, "op_odd", 3, bs=3, cams=2, level_hw=[(7, 9), (5, 3)], C=48, G=3, A=7, P=3)
-    module_case(regs, blocks, ops, "module_det", 4, "det", embed=64, G=8,
+    if want("op_small"):
+        op_case(blocks, "op_small", 1, bs=2, cams=3, level_hw=[(12, 20), (6, 10), (3, 5)], C=32, G=4, A=10, P=5)
+    if want("op_c256"):
+        op_case(blocks, "op_c256", 2, bs=1, cams=6, level_hw=[(8, 12), (4, 6), (2, 3), (1, 2)], C=256, G=8, A=12, P=13)
+    if want("op_odd"):
+        op_case(blocks, "op_odd", 3, bs=3, cams=2, level_hw=[(7, 9), (5, 3)], C=48, G=3, A=7, P=3)
+    if want("module_det"):
+        module_case(regs, blocks, ops, "module_det", 4, "det", embed=64, G=8,
                 level_hw=[(16, 44), (8, 22), (4, 11)], final_hw=(64, 176), n_keep=24)
-    module_case(regs, blocks, ops, "module_plan", 5, "plan", embed=32, G=4,
+    if want("module_plan"):
+        module_case(regs, blocks, ops, "module_plan", 5, "plan", embed=32, G=4,
                 level_hw=[(16, 44), (8, 22), (4, 11)], final_hw=(64, 176), n_keep=8, via_oracle_daf=True)
-    module_case(regs, blocks, ops, "module_det_daf", 6, "det", embed=32, G=4,
+    if want("module_det_daf"):
+        module_case(regs, blocks, ops, "module_det_daf", 6, "det", embed=32, G=4,
                 level_hw=[(16, 44), (8, 22), (4, 11)], final_hw=(64, 176), n_keep=24, bs=2,
                 via_oracle_daf=True)
+    # the shipped layout (C=256, G=8, 4 levels) through the reference's own torch branch, det and plan kinds
+    if want("module_det_c256"):
+        module_case(regs, blocks, ops, "module_det_c256", 7, "det", embed=256, G=8,
+                level_hw=[(8, 22), (4, 11), (2, 6), (1, 3)], final_hw=(64, 176), n_keep=8, store_f16=True)
+    if want("module_plan_c256"):
+        module_case(regs, blocks, ops, "module_plan_c256", 8, "plan", embed=256, G=8,
+                level_hw=[(8, 22), (4, 11), (2, 6), (1, 3)], final_hw=(64, 176), n_keep=6, store_f16=True, allow_band=True)
 
 
 if __name__ == "__main__":

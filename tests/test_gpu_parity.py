@@ -319,7 +319,7 @@ def _load_module_golden(name):
     return d, m.cuda().eval(), L
 
 
-@pytest.mark.parametrize("name", ["module_det", "module_plan", "module_det_daf"])
+@pytest.mark.parametrize("name", ["module_det", "module_plan", "module_det_daf", "module_det_c256"])
 @pytest.mark.parametrize("fused", [True, False])
 def test_module_matches_reference_module(ops, name, fused):
     """Whole DeformableFeatureAggregation.forward (key points -> weights -> projection -> op ->
@@ -327,7 +327,7 @@ def test_module_matches_reference_module(ops, name, fused):
     the reference's own state_dict loaded strictly."""
     d, m, L = _load_module_golden(name)
     m.fused_inference = fused
-    fmaps = [torch.tensor(d[f"fmap{i}"]).cuda() for i in range(L)]
+    fmaps = [torch.tensor(d[f"fmap{i}"]).float().cuda() for i in range(L)]
     fm = ops.feature_maps_format(fmaps)
     metas = dict(projection_mat=dev(d["projection_mat"]), image_wh=dev(d["image_wh"]))
     with torch.no_grad():

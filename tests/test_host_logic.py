@@ -36,12 +36,12 @@ def build_module(d, use_deformable_func):
     return m.eval(), L
 
 
-@pytest.mark.parametrize("name", ["module_det", "module_plan", "module_det_daf"])
+@pytest.mark.parametrize("name", ["module_det", "module_plan", "module_det_daf", "module_det_c256", "module_plan_c256"])
 def test_feature_maps_format_matches_reference(name):
     import hipad_b200
     d = np.load(os.path.join(GOLD, name + ".npz"))
     L = len([k for k in d.files if k.startswith("fmap")])
-    fmaps = [torch.tensor(d[f"fmap{i}"]) for i in range(L)]
+    fmaps = [torch.tensor(d[f"fmap{i}"]).float() for i in range(L)]      # (the C=256 fixtures store fp16-exact values)
     col, shapes, starts = hipad_b200.feature_maps_format(fmaps)
     assert list(col.shape) == d["col_feats_shape"].tolist()
     assert shapes.dtype == torch.int64 and starts.dtype == torch.int64
@@ -70,7 +70,7 @@ def test_feature_maps_format_camera_groups():
     assert all(torch.equal(a, b) for a, b in zip(back[1], grp_b))
 
 
-@pytest.mark.parametrize("name", ["module_det", "module_plan", "module_det_daf"])
+@pytest.mark.parametrize("name", ["module_det", "module_plan", "module_det_daf", "module_det_c256", "module_plan_c256"])
 def test_key_points_weights_and_projection_match_reference(name):
     d = np.load(os.path.join(GOLD, name + ".npz"))
     m, L = build_module(d, use_deformable_func=False)
@@ -85,11 +85,14 @@ def test_key_points_weights_and_projection_match_reference(name):
     assert rel_err(p2d.numpy(), d["points_2d"]) <= 1e-5
 
 
-def test_module_torch_branch_matches_reference_module():
-    """use_deformable_func=False is the reference's own pure-torch branch, kept as an explicit opt-in."""
-    d = np.load(os.path.join(GOLD, "module_det.npz"))
+@pytest.mark.parametrize("name", ["module_det", "module_det_c256", "module_plan_c256"])
+def test_module_torch_branch_matches_reference_module(name):
+    """use_deformable_func=False is the reference's own pure-torch branch, kept as an explicit opt-in.  The C=256
+    fixtures are the shipped layout (G=8, 4 levels) run through the unmodified reference's torch branch, det and plan."""
+    d = np.load(os.path.join(GOLD, name + ".npz"))
+    assert not bool(d["via_oracle_daf"])
     m, L = build_module(d, use_deformable_func=False)
-    fmaps = [torch.tensor(d[f"fmap{i}"]) for i in range(L)]
+    fmaps = [torch.tensor(d[f"fmap{i}"]).float() for i in range(L)]
     metas = dict(projection_mat=torch.tensor(d["projection_mat"]), image_wh=torch.tensor(d["image_wh"]))
     with torch.no_grad():
         out = m(torch.tensor(d["instance_feature"]), torch.tensor(d["anchor"]), torch.tensor(d["anchor_embed"]),
