@@ -722,7 +722,8 @@ def decoder_legs(args, dev, world, rank, max_over_ranks):
         return {"error": repr(e)[:200]}, None
     fwd = tr = None
     try:
-        variants = ("reference", "ours", "ours_module") if (rank == 0 and world == 1) else ("ours_module",)
+        variants = (("reference", "ours", "ours_module", "ours_module_graph") if (rank == 0 and world == 1)
+                    else ("ours_module_graph",))
         r = bench_decoder.run(hw_list=((352, 640), (256, 704)) if world == 1 else ((352, 640),), frames=args.decoder_frames,
                               bs=1, variants=variants)
         for hw, d in r.items():

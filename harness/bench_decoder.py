@@ -4,6 +4,7 @@ deformable attention), bs=1 inference, through the UNMODIFIED reference decoder 
   reference    the reference's own ops package over its own CUDA op rebuilt for sm_100a (oracle/_ref)
   ours         hipad_b200.ops plugged in (5-argument op, reference module code around it)
   ours_module  hipad_b200.ops + hipad_b200.DeformableFeatureAggregation (fused projection + softmax + aggregation)
+  ours_module_graph  the same, every module call replayed as one CUDA graph (module.graph_inference)
 Times >= `frames` consecutive frames after 2 warm-up frames (temporal caches populated), CUDA events per frame, and
 reports the DFA share of a forward (CUDA events around every aggregation call).  Prints one JSON object.
 """
@@ -82,7 +83,8 @@ def dfa_share(dec, hw, bs=1, device="cuda", frames=5):
             "dfa_share": round(dfa_ms / all_ms, 3)}
 
 
-def run(hw_list=((352, 640), (256, 704)), frames=30, bs=1, variants=("reference", "ours", "ours_module")):
+def run(hw_list=((352, 640), (256, 704)), frames=30, bs=1,
+        variants=("reference", "ours", "ours_module", "ours_module_graph")):
     from oracle import build_ref
     res = {}
     for hw in hw_list:

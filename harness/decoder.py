@@ -10,12 +10,13 @@ deformable_aggregation_function as DAF`` and ``models/{sparse_detector,ego/insta
 import ``feature_maps_format`` from the same package, so registering a module under
 ``sys.modules['projects.mmdet3d_plugin.ops']`` before importing ``models`` swaps the op.
 
-Three variants of the op package:
+Variants of the op package:
   "reference"  the reference's own ops/*.py (vendored) over its own CUDA extension rebuilt for sm_100a
                (oracle/_ref/deformable_aggregation_ext.so, oracle/build_ref.py)
   "ours"       hipad_b200.ops (same decoder, same DeformableFeatureAggregation module class as the reference)
   "ours_module" hipad_b200.ops AND hipad_b200.DeformableFeatureAggregation registered in the ATTENTION registry
                under the reference's name (the fused inference path / grouped launches are then what runs)
+  "ours_module_graph" the same with the module's CUDA-graph inference forward switched on (graph_inference)
   any module object: used as given (tests pass a torch emulation for CPU runs)
 """
 import importlib
@@ -128,10 +129,10 @@ def load_models(ops="ours"):
         kind = ops
         if kind == "reference":
             ops_mod = reference_ops_module(root)
-        elif kind in ("ours", "ours_module"):
+        elif kind in ("ours", "ours_module", "ours_module_graph"):
             import hipad_b200
             ops_mod = hipad_b200.ops
-            want_module = kind == "ours_module"
+            want_module = kind != "ours"
         else:
             raise ValueError(kind)
     else:
@@ -177,6 +178,11 @@ def build_decoder(ops="ours", hw=(352, 640), seed=0, device="cpu", weights_fc_st
                 m.weight.copy_(torch.randn(m.weight.shape, generator=g) * weights_fc_std)
                 m.bias.copy_(torch.randn(m.bias.shape, generator=g) * weights_fc_std)
     dec = dec.to(device).eval()
+    if ops == "ours_module_graph":      # our module replays its inference forward as one CUDA graph per call
+        import hipad_b200
+        for m in dec.modules():
+            if isinstance(m, hipad_b200.DeformableFeatureAggregation):
+                m.graph_inference = True
     dec._hipad_ops = counted
     dec._hipad_models = models
     return dec

@@ -17,6 +17,8 @@ Compute paths of ``forward`` (selected by the same ``use_deformable_func`` flag 
         branch, kept because it is part of the module's documented interface.  It is an explicit
         opt-in, never selected automatically, and is NOT a fallback for a missing CUDA library.
 """
+import os
+import weakref
 from typing import List, Optional
 
 import torch
@@ -97,7 +99,7 @@ class SparseBox3DKeyPointsGenerator(nn.Module):
         # NB: DeformableFeatureAggregation calls this as (anchor, anchor_embed, instance_feature):
         # the learnable offsets are driven by the anchor embedding.
         bs, num_anchor = anchor.shape[:2]
-        size = anchor[..., None, [W, L, H]].exp()
+        size = anchor[..., None, W:H + 1].exp()        # (W, L, H) are adjacent: a slice, no index tensor to upload
         key_points = self.fix_scale * size
         if self.num_learnable_pts > 0 and instance_feature is not None:
             scale = self.learnable_fc(instance_feature).reshape(bs, num_anchor, self.num_learnable_pts, 3)
@@ -105,7 +107,7 @@ class SparseBox3DKeyPointsGenerator(nn.Module):
         cos, sin = anchor[..., None, COS_YAW], anchor[..., None, SIN_YAW]
         kx, ky, kz = key_points.unbind(-1)
         key_points = torch.stack([cos * kx - sin * ky, sin * kx + cos * ky, kz], dim=-1)
-        key_points = key_points + anchor[..., None, [X, Y, Z]]
+        key_points = key_points + anchor[..., None, X:Z + 1]
 
         if (cur_timestamp is None or temp_timestamps is None or T_cur2temp_list is None
                 or len(temp_timestamps) == 0):
@@ -141,6 +143,8 @@ class SparsePoint3DKeyPointsGenerator(nn.Module):
             self.learnable_fc = nn.Linear(embed_dims, self.num_pts * 2)
         self.fix_height = tuple(float(h) for h in fix_height)
         self.ground_height = ground_height
+        # device copy of fix_height (not in the state dict): no host-to-device upload per call, graph-capturable
+        self.register_buffer("_fix_height_t", torch.tensor(self.fix_height, dtype=torch.float32), persistent=False)
 
     def init_weight(self):
         if self.num_learnable_pts > 0:
@@ -161,7 +165,7 @@ class SparsePoint3DKeyPointsGenerator(nn.Module):
             src = instance_feature
         offset = self.learnable_fc(src).reshape(bs, num_anchor, self.num_sample, n_h, self.num_learnable_pts, 2)
         xy = offset + anchor.view(bs, num_anchor, self.num_sample, 1, 1, 2)
-        heights = xy.new_tensor(self.fix_height).view(1, 1, 1, n_h, 1, 1)
+        heights = self._fix_height_t.to(dtype=xy.dtype).view(1, 1, 1, n_h, 1, 1)
         z = (xy.new_full(xy.shape[:-1] + (1,), float(self.ground_height)) + heights)
         key_points = torch.cat([xy, z], dim=-1).flatten(2, 4)
 
@@ -206,6 +210,9 @@ class DeformableFeatureAggregation(nn.Module):
         self.use_deformable_func = use_deformable_func
         self.use_temporal_anchor_embed = use_temporal_anchor_embed
         self.fused_inference = fused_inference
+        # replay the inference forward as one CUDA graph per input signature (set the attribute, or HIPAD_MODULE_GRAPH=1)
+        self.graph_inference = os.environ.get("HIPAD_MODULE_GRAPH", "0") not in ("", "0")
+        self._graphs = {}
         self.attn_drop = attn_drop
         self.residual_mode = residual_mode
         self.proj_drop = nn.Dropout(proj_drop)
@@ -255,6 +262,47 @@ class DeformableFeatureAggregation(nn.Module):
     # ------------------------------------------------------------------ forward
     def forward(self, instance_feature: torch.Tensor, anchor: torch.Tensor, anchor_embed: torch.Tensor,
                 feature_maps: List[torch.Tensor], metas: dict, **kwargs):
+        if (self.graph_inference and self.use_deformable_func and not self.training and not torch.is_grad_enabled()
+                and instance_feature.is_cuda and not torch.cuda.is_current_stream_capturing()):
+            return self._graphed_forward(instance_feature, anchor, anchor_embed, feature_maps, metas)
+        return self._forward_impl(instance_feature, anchor, anchor_embed, feature_maps, metas)
+
+    def _graphed_forward(self, instance_feature, anchor, anchor_embed, feature_maps, metas):
+        """Inference forward as ONE CUDA-graph launch (row f4, decoder glue).  The eager forward is ~40 small launches
+        (key points, camera embedding, ``weights_fc``, projection, aggregation, ``output_proj``): host-bound at bs=1.
+        A graph is captured per input signature on static copies of the inputs; a call copies its (small) inputs in,
+        replays, and returns a copy of the static output.  The feature maps live in ONE static buffer per shape shared
+        by every module (refreshed when a different ``col_feats`` tensor, or a new version of it, is passed in).
+        Same kernels, same arithmetic, bitwise the eager result."""
+        wh = metas.get("image_wh")
+        ins = (instance_feature, anchor, anchor_embed, metas["projection_mat"]) + ((wh,) if wh is not None else ())
+        ins = tuple(t.contiguous() for t in ins)
+        static_maps = _static_feature_maps(feature_maps)
+        key = tuple((tuple(t.shape), t.dtype) for t in ins) + (static_maps[0].data_ptr(),)
+        ent = self._graphs.get(key)
+        if ent is None:
+            statics = tuple(torch.empty_like(t) for t in ins)
+            for d, t in zip(statics, ins):
+                d.copy_(t)
+            s_metas = {"projection_mat": statics[3], "image_wh": statics[4] if wh is not None else None}
+            run = lambda: self._forward_impl(statics[0], statics[1], statics[2], static_maps, s_metas)
+            side = torch.cuda.Stream(device=instance_feature.device)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):        # warm-up outside the capture (lazy module / library initialisation)
+                run()
+            torch.cuda.current_stream().wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            # the graphs of one module share a memory pool (one replays at a time and its output is copied out)
+            pool = next(iter(self._graphs.values()))[0].pool() if self._graphs else None
+            with torch.cuda.graph(graph, pool=pool):
+                out = run()
+            ent = self._graphs[key] = (graph, list(statics), out)
+        graph, statics, out = ent
+        torch._foreach_copy_(statics, list(ins))
+        graph.replay()
+        return out.clone()
+
+    def _forward_impl(self, instance_feature, anchor, anchor_embed, feature_maps, metas):
         bs, num_anchor = instance_feature.shape[:2]
         key_points = self.kps_generator(anchor, anchor_embed, instance_feature)
 
@@ -366,6 +414,32 @@ class DeformableFeatureAggregation(nn.Module):
         grouped = features.reshape(features.shape[:-1] + (self.num_groups, self.group_dims))
         fused = (weights[..., None] * grouped).sum(dim=2).sum(dim=2)
         return fused.reshape(bs, num_anchor, self.num_pts, self.embed_dims)
+
+
+_STATIC_MAPS = {}      # (device, dtype, col shape, table shape) -> static [col_feats, spatial_shape, scale_start_index] + source tag
+
+
+def _static_feature_maps(feature_maps):
+    """Static device copies of the ``feature_maps_format`` triple for graph replay.  The copy (one device-to-device
+    pass over the maps, ~40 us for a stage-2 frame) runs when the triple's tensors are not the ones copied last: a new
+    tensor object per frame (what ``feature_maps_format`` returns) or an in-place update that bumps ``_version``."""
+    col, shapes, starts = feature_maps[0], feature_maps[1], feature_maps[2]
+    key = (col.device, col.dtype, tuple(col.shape), tuple(shapes.shape))
+    ent = _STATIC_MAPS.get(key)
+    if ent is None:
+        ent = _STATIC_MAPS[key] = dict(
+            maps=[torch.empty_like(col.contiguous()),
+                  torch.empty(tuple(shapes.shape), dtype=torch.int32, device=col.device),
+                  torch.empty(tuple(starts.shape), dtype=torch.int32, device=col.device)],
+            src=None, versions=None)
+    same = ent["src"] is not None and all(r() is t for r, t in zip(ent["src"], (col, shapes, starts)))
+    versions = (col._version, shapes._version, starts._version)
+    if not same or ent["versions"] != versions:
+        for d, t in zip(ent["maps"], (col, shapes, starts)):
+            d.copy_(t)
+        ent["src"] = tuple(weakref.ref(t) for t in (col, shapes, starts))
+        ent["versions"] = versions
+    return ent["maps"]
 
 
 def aggregate_layer(calls, feature_maps, metas):

@@ -335,6 +335,44 @@ def test_module_matches_reference_module(ops, name, fused):
     assert rel_err(out.cpu().numpy(), d["out"]) <= 2e-5
 
 
+@pytest.mark.parametrize("name", ["module_det", "module_det_c256"])
+def test_module_graph_inference_equals_eager(ops, name):
+    """graph_inference: the module's inference forward replayed as one CUDA graph.  Bitwise the eager result, across
+    changed inputs, a NEW feature tensor (new frame), an in-place update of the same tensor, and a second signature."""
+    d, m, L = _load_module_golden(name)
+    fmaps = [torch.tensor(d[f"fmap{i}"]).float().cuda() for i in range(L)]
+    metas = dict(projection_mat=dev(d["projection_mat"]), image_wh=dev(d["image_wh"]))
+    inst, anchor, emb = dev(d["instance_feature"]), dev(d["anchor"]), dev(d["anchor_embed"])
+    g = torch.Generator(device="cuda").manual_seed(3)
+
+    def both(inst_, anchor_, emb_, fm_):
+        with torch.no_grad():
+            m.graph_inference = False
+            want = m(inst_, anchor_, emb_, fm_, metas)
+            m.graph_inference = True
+            got = m(inst_, anchor_, emb_, fm_, metas)
+        assert torch.equal(want, got)
+        return got
+
+    fm = ops.feature_maps_format(fmaps)
+    first = both(inst, anchor, emb, fm)
+    assert rel_err(first.cpu().numpy(), d["out"]) <= 2e-5
+    assert len(m._graphs) == 1
+    both(inst + 0.25 * torch.randn(inst.shape, device="cuda", generator=g), anchor, emb, fm)          # new inputs, replay
+    fm2 = ops.feature_maps_format([f * 0.5 + 1.0 for f in fmaps])                                     # a new frame
+    second = both(inst, anchor, emb, fm2)
+    assert not torch.equal(first, second)
+    fm2[0].mul_(2.0)                                                                                  # in-place update
+    third = both(inst, anchor, emb, fm2)
+    assert not torch.equal(second, third)
+    both(inst[:, :5].contiguous(), anchor[:, :5].contiguous(), emb[:, :5].contiguous(), fm2)           # second signature
+    assert len(m._graphs) == 2
+    both(inst, anchor, emb, fm)                                                                       # back to frame one
+    m.train()                                                                                         # training: eager path
+    out = m(inst, anchor, emb, fm, metas)
+    assert out.requires_grad and len(m._graphs) == 2
+
+
 def test_module_training_path_backward(ops):
     d, m, L = _load_module_golden("module_det")
     m.train()
