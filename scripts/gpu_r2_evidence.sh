@@ -25,6 +25,8 @@ timeout 900 ncu --set full --clock-control none --import-source on -k regex:dfa_
 ncu -i /tmp/full_group.ncu-rep --page raw --csv 2>/dev/null | gzip -9 > $OUT/full_layer_raw.csv.gz
 ncu -i /tmp/full_group.ncu-rep --page source --csv 2>/dev/null | gzip -9 > $OUT/full_layer_source.csv.gz
 python profiles/summarize_ncu.py /tmp/full_group.ncu-rep > $OUT/full_layer_summary.txt 2>&1
+nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o /tmp/l2_gather_peak profiles/micro/l2_gather_peak.cu && /tmp/l2_gather_peak > $OUT/l2_gather_peak.json; echo "l2 peak rc=$?" | tee -a $OUT/status.txt
+python profiles/gather_roofline.py $OUT/full_layer_raw.csv.gz $OUT/l2_gather_peak.json $OUT/gather_roofline.json > /dev/null 2>> $OUT/ncu_full.log
 python profiles/prof_percall.py 2 > $OUT/plain_percall.log 2>&1 && \
 timeout 900 ncu --set full --clock-control none -k regex:dfa_ --launch-skip 25 -c 25 -f -o /tmp/full_percall \
     python profiles/prof_percall.py 2 > $OUT/ncu_percall.log 2>&1; echo "ncu percall rc=$?" | tee -a $OUT/status.txt
