@@ -273,12 +273,14 @@ class DeformableFeatureAggregation(nn.Module):
         A graph is captured per input signature on static copies of the inputs; a call copies its (small) inputs in,
         replays, and returns a copy of the static output.  The feature maps live in ONE static buffer per shape shared
         by every module (refreshed when a different ``col_feats`` tensor, or a new version of it, is passed in).
-        Same kernels, same arithmetic, bitwise the eager result."""
+        Same kernels, same arithmetic, bitwise the eager result.  Graphs are dropped when the module is moved or cast
+        (``_apply``); replacing a parameter tensor of a sub-module by hand, or driving one module from several host
+        threads, is not supported while ``graph_inference`` is on."""
         wh = metas.get("image_wh")
         ins = (instance_feature, anchor, anchor_embed, metas["projection_mat"]) + ((wh,) if wh is not None else ())
         ins = tuple(t.contiguous() for t in ins)
         static_maps = _static_feature_maps(feature_maps)
-        key = tuple((tuple(t.shape), t.dtype) for t in ins) + (static_maps[0].data_ptr(),)
+        key = tuple((tuple(t.shape), t.dtype) for t in ins) + (static_maps[0].data_ptr(), torch.is_autocast_enabled())
         ent = self._graphs.get(key)
         if ent is None:
             statics = tuple(torch.empty_like(t) for t in ins)
@@ -301,6 +303,16 @@ class DeformableFeatureAggregation(nn.Module):
         torch._foreach_copy_(statics, list(ins))
         graph.replay()
         return out.clone()
+
+    def _apply(self, fn, *args, **kwargs):
+        # .to() / .cuda() / .half() ... replace the parameter tensors the captured graphs point at
+        self._graphs = {}
+        return super()._apply(fn, *args, **kwargs)
+
+    def __getstate__(self):
+        state = self.__dict__.copy()        # deepcopy / pickle of a module: captured graphs stay behind
+        state["_graphs"] = {}
+        return state
 
     def _forward_impl(self, instance_feature, anchor, anchor_embed, feature_maps, metas):
         bs, num_anchor = instance_feature.shape[:2]

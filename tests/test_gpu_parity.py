@@ -371,6 +371,13 @@ def test_module_graph_inference_equals_eager(ops, name):
     m.train()                                                                                         # training: eager path
     out = m(inst, anchor, emb, fm, metas)
     assert out.requires_grad and len(m._graphs) == 2
+    m.eval()
+    m.float()                                     # moving / casting the module drops the captured graphs
+    assert len(m._graphs) == 0
+    both(inst, anchor, emb, fm)
+    assert len(m._graphs) == 1
+    import copy
+    assert len(copy.deepcopy(m)._graphs) == 0     # and they do not travel with a copy of the module
 
 
 def test_module_training_path_backward(ops):
