@@ -577,10 +577,60 @@ __global__ void __launch_bounds__(kW * 32, kMinCtas) dfa_group_kernel(const Grou
             if (s_flag[0]) {
                 __threadfence();
                 const float* parts = p.partial + ((size_t)gc.part_begin + (size_t)ba * S) * CPAD;
-                for (int ch = tid; ch < CPAD; ch += kThreads) {
-                    float s = 0.f;
-                    for (int q = 0; q < S; ++q) s += __ldcg(parts + (size_t)q * CPAD + ch);
-                    out_row[ch] = s;
+                // The S partial rows are contiguous: they are staged in this CTA's (now dead) shared-memory tables by bulk
+                // asynchronous copies (cp.async.bulk + mbarrier: one thread issues up to ~18 KB, one round trip per chunk
+                // instead of one per few slices) and added from there in slice order.
+                constexpr int kRowBytes = CPAD * 4;
+                constexpr int kChPer = (CPAD + kThreads - 1) / kThreads;
+                float* stage = reinterpret_cast<float*>(smem_raw + so.lxy);
+                const int cap_rows = (so.total - so.lxy) / kRowBytes;
+                if (cap_rows >= 2 && (reinterpret_cast<uintptr_t>(parts) & 15) == 0) {
+                    const unsigned bar_a = (unsigned)__cvta_generic_to_shared(s_wcnt);       // 8-byte aligned, dead by now
+                    const unsigned stage_a = (unsigned)__cvta_generic_to_shared(stage);
+                    if (tid == 0) {
+                        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_a), "r"(1) : "memory");
+                        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+                    }
+                    float acc_s[kChPer];
+#pragma unroll
+                    for (int c2 = 0; c2 < kChPer; ++c2) acc_s[c2] = 0.f;
+                    unsigned phase = 0;
+                    for (int q0 = 0; q0 < S; q0 += cap_rows) {
+                        const int nr = min(cap_rows, S - q0);
+                        __syncthreads();         // barrier initialised / previous chunk consumed; the tables are dead
+                        if (tid == 0) {
+                            const unsigned bytes = (unsigned)nr * (unsigned)kRowBytes;
+                            // generic-proxy accesses (this CTA's earlier use of the tables; the other slices' partial rows,
+                            // acquired through the ticket) before the async-proxy copy
+                            asm volatile("fence.proxy.async;" ::: "memory");
+                            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(bytes) : "memory");
+                            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                         ::"r"(stage_a), "l"(parts + (size_t)q0 * CPAD), "r"(bytes), "r"(bar_a) : "memory");
+                        }
+                        unsigned ok = 0;
+                        do {
+                            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                                         : "=r"(ok) : "r"(bar_a), "r"(phase) : "memory");
+                        } while (!ok);
+                        phase ^= 1u;
+#pragma unroll
+                        for (int c2 = 0; c2 < kChPer; ++c2) {
+                            const int ch = tid + c2 * kThreads;
+                            if (ch < CPAD)
+                                for (int q = 0; q < nr; ++q) acc_s[c2] += stage[q * CPAD + ch];
+                        }
+                    }
+#pragma unroll
+                    for (int c2 = 0; c2 < kChPer; ++c2) {
+                        const int ch = tid + c2 * kThreads;
+                        if (ch < CPAD) out_row[ch] = acc_s[c2];
+                    }
+                } else {
+                    for (int ch = tid; ch < CPAD; ch += kThreads) {
+                        float s = 0.f;
+                        for (int q = 0; q < S; ++q) s += __ldcg(parts + (size_t)q * CPAD + ch);
+                        out_row[ch] = s;
+                    }
                 }
             }
         }
