@@ -160,3 +160,27 @@ def test_reference_arm_prints_one_json_line():
     sys.path.insert(0, root)
     import bench
     assert d["config"] == bench.shared_config(1, "f32")
+
+
+def test_static_feature_maps_refresh_policy():
+    """graph_inference reads the feature maps from one static buffer per shape: refreshed for a new tensor object (a new
+    frame) and for an in-place update of the same tensor, left alone when the same triple comes back (host logic only)."""
+    from hipad_b200 import blocks
+    blocks._STATIC_MAPS.clear()
+    col = torch.arange(24, dtype=torch.float32).reshape(1, 6, 4)
+    shapes = torch.tensor([[[2, 3]]], dtype=torch.int64)
+    starts = torch.tensor([[0]], dtype=torch.int64)
+    s1 = blocks._static_feature_maps([col, shapes, starts])
+    assert torch.equal(s1[0], col) and s1[1].dtype == torch.int32 and torch.equal(s1[1].long(), shapes)
+    s1[0].fill_(-1.0)                                   # scribble: a second call with the SAME triple must not copy again
+    s2 = blocks._static_feature_maps([col, shapes, starts])
+    assert s2[0] is s1[0] and float(s2[0].sum()) == -24.0
+    col.add_(1.0)                                       # in-place update bumps the version: refreshed
+    s3 = blocks._static_feature_maps([col, shapes, starts])
+    assert s3[0] is s1[0] and torch.equal(s3[0], col)
+    col2 = col.clone() * 2                              # a new frame: new tensor object, same shape -> same buffer, new content
+    s4 = blocks._static_feature_maps([col2, shapes, starts])
+    assert s4[0] is s1[0] and torch.equal(s4[0], col2)
+    other = blocks._static_feature_maps([torch.zeros(1, 8, 4), shapes, starts])      # another shape: another buffer
+    assert other[0] is not s1[0]
+    blocks._STATIC_MAPS.clear()
