@@ -7,7 +7,7 @@
  * no hidden device allocation: the caller owns every buffer,
  * including the workspaces.  All launches go to the given stream (the
  * backward additionally forks part of its work onto one helper stream per caller
- * stream, created on first use, joined before the call returns on every path, and kept for the life of
+ * stream, created on first use at the device's highest stream priority, joined before the call returns on every path, and kept for the life of
  * the process: the only process-wide state; a caller stream must be driven by one host thread at a time,
  * and cudaStreamPerThread callers run the backward without the helper) and are
  * CUDA-graph capturable (no host synchronisation, no legacy-stream use).
